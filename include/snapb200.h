@@ -1,0 +1,142 @@
+/*
+ * snapb200.h -- C ABI of the B200-native Snappy codec (libsnapb200.so).
+ *
+ * This is the drop-in boundary for rust-snappy's raw/frame hot path: a Rust
+ * `snap` shim (rust/) binds exactly these symbols. Each
+ * entry point cites the reference interface it replaces (paths relative to the
+ * rust-snappy checkout). Plain pointers and sizes only -- no torch/CUDA types.
+ *
+ * All work is done by sm_100a CUDA kernels; there is NO CPU fallback. When no
+ * CUDA device is usable every compute call returns SB_E_NO_DEVICE.
+ */
+#ifndef SNAPB200_H
+#define SNAPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* snap::Error variant index (declaration order of src/error.rs:72-180) plus
+ * the payload fields of that variant in a, b, c. 0 = Ok. */
+enum {
+    SB_OK = 0,
+    SB_TOO_BIG = 1,                  /* a=given  b=max                         */
+    SB_BUFFER_TOO_SMALL = 2,         /* a=given  b=min                         */
+    SB_EMPTY = 3,
+    SB_HEADER = 4,
+    SB_HEADER_MISMATCH = 5,          /* a=expected_len b=got_len               */
+    SB_LITERAL = 6,                  /* a=len a=src_len c=dst_len              */
+    SB_COPY_READ = 7,                /* a=len b=src_len                        */
+    SB_COPY_WRITE = 8,               /* a=len b=dst_len                        */
+    SB_OFFSET = 9,                   /* a=offset b=dst_pos                     */
+    SB_STREAM_HEADER = 10,           /* a=byte                                 */
+    SB_STREAM_HEADER_MISMATCH = 11,  /* a=6 body bytes, little endian          */
+    SB_UNSUPPORTED_CHUNK_TYPE = 12,  /* a=byte                                 */
+    SB_UNSUPPORTED_CHUNK_LENGTH = 13,/* a=len b=header(0/1)                    */
+    SB_CHECKSUM = 14,                /* a=expected b=got                       */
+    SB_IO_UNEXPECTED_EOF = 100,      /* io::ErrorKind::UnexpectedEof (read_exact, src/read.rs:439-455) */
+    /* library-level failures (never produced by the reference) */
+    SB_E_NO_DEVICE = 200,            /* no usable CUDA device / kernel image   */
+    SB_E_CUDA = 201,                 /* a=cudaError_t                          */
+    SB_E_INVALID = 202               /* bad argument (null pointer, ...)       */
+};
+
+typedef struct sb_error {
+    uint32_t code;
+    uint32_t _pad;
+    uint64_t a, b, c;
+} sb_error;
+
+/* ---- scalar API: host pointers, mirrors snap::raw ------------------------ */
+
+/* snap::raw::max_compress_len  (src/compress.rs:42-53). Pure arithmetic. */
+size_t sb_max_compress_len(size_t input_len);
+
+/* snap::raw::Encoder::compress (src/compress.rs:99-154): `in` is compressed
+ * as ONE raw stream (varint header + 64KB blocks) into out[..cap]; on success
+ * returns 0 and *out_n = bytes written. Errors: TooBig, BufferTooSmall. */
+int sb_compress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_n, sb_error* err);
+
+/* snap::raw::decompress_len (src/decompress.rs:30-35). Header parse only. */
+int sb_decompress_len(const uint8_t* in, size_t n, size_t* out_len, sb_error* err);
+
+/* snap::raw::Decoder::decompress (src/decompress.rs:75-95). Exact error
+ * variant and payload of the reference on corrupt input. */
+int sb_decompress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_n, sb_error* err);
+
+/* crc32::CheckSummer::crc32c_masked (src/crc32.rs:35-38), computed on device. */
+int sb_crc32c_masked(const uint8_t* in, size_t n, uint32_t* out, sb_error* err);
+
+/* ---- batched host API: many independent raw streams per call -------------
+ * What a Rust caller holding many buffers (or the frame writers below) uses:
+ * one call, pinned staging + H2D/D2H pipelined against the kernels inside.
+ * Unit i reads in_base[in_offs[i] .. +in_lens[i]) and writes out_base[out_offs[i] ..];
+ * out capacity per unit is out_caps[i]. statuses may be NULL for compress. */
+int sb_compress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, const uint32_t* in_lens,
+                           uint8_t* out_base, const uint64_t* out_offs, const uint32_t* out_caps,
+                           uint32_t* out_lens, size_t count, sb_error* err);
+int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, const uint32_t* in_lens,
+                             uint8_t* out_base, const uint64_t* out_offs, const uint32_t* out_caps,
+                             uint32_t* out_lens, sb_error* statuses, size_t count, sb_error* err);
+
+/* ---- batched device API: device pointers, stream ordered ------------------
+ * The kernels' native interface (and what bench.py's `value` times). All
+ * pointers are device pointers; `stream` is a cudaStream_t passed as void*.
+ * Addressing is base + i*stride (uniform) -- or per-unit pointer arrays when
+ * in_ptrs/out_ptrs are non-NULL. in_lens/out_caps NULL => the uniform value. */
+typedef struct sb_batch {
+    const uint8_t* const* in_ptrs;  const uint8_t* in_base;  uint64_t in_stride;
+    const uint32_t* in_lens;        uint32_t in_len_uniform;
+    uint8_t* const* out_ptrs;       uint8_t* out_base;       uint64_t out_stride;
+    const uint32_t* out_caps;       uint32_t out_cap_uniform;
+    uint32_t* out_lens;             /* device, count entries (required)      */
+    sb_error* statuses;             /* device, count entries (decode; may be NULL for encode) */
+    uint32_t count;
+} sb_batch;
+
+/* Each unit (<= 4 GiB - 1) becomes one raw stream exactly as Encoder::compress
+ * would produce it. Units of <= 65536 bytes are one block per CTA. */
+int sb_compress_batch_device(const sb_batch* batch, void* stream, sb_error* err);
+/* Each unit is one raw stream; statuses[i] carries the reference's error. */
+int sb_decompress_batch_device(const sb_batch* batch, void* stream, sb_error* err);
+/* Masked CRC-32C of each unit (frame chunks): out_lens[i] receives the CRC. */
+int sb_crc32c_masked_batch_device(const sb_batch* batch, void* stream, sb_error* err);
+
+/* ---- frame format (snap::write::FrameEncoder / snap::read::FrameDecoder) --
+ * One-shot forms over host memory. sb_frame_encode(in) produces exactly the
+ * bytes of `FrameEncoder::new(vec![]).write_all(in); into_inner()`
+ * (src/write.rs:123-192): stream identifier + one chunk per <=65536-byte slice;
+ * empty input => empty output. */
+size_t sb_frame_max_len(size_t n);
+int sb_frame_encode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_n, sb_error* err);
+/* The chunk loop of write::Inner::write alone (src/write.rs:171-190): chunks for
+ * `in` with (include_ident=1) or without the leading stream identifier -- what
+ * a streaming FrameEncoder calls for every buffer it hands down. */
+int sb_frame_encode_ex(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_n, int include_ident, sb_error* err);
+/* `FrameDecoder::new(in).read_to_end()` (src/read.rs:104-239): pass out=NULL to
+ * size the output (*out_n). Errors carry the reference's variant/payload. */
+int sb_frame_decode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_n, sb_error* err);
+
+/* Device-resident frame encode of n bytes at d_in (device) into d_out (device,
+ * cap >= sb_frame_max_len(n)); *out_n (host) = stream length. include_ident=0
+ * omits the 10-byte stream identifier (ranks > 0 of a sharded stream). */
+int sb_frame_encode_device(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap,
+                           int include_ident, uint64_t* out_n, void* stream, sb_error* err);
+
+/* ---- misc ---------------------------------------------------------------- */
+/* Number of kernel launches issued by this library since load (bench.py's
+ * gpu_launches evidence). */
+uint64_t sb_launch_count(void);
+/* Device-side helper used by tests/bench: fills unit i (i < count) at
+ * d_out + i*stride with text[off_i .. off_i+len), off_i = ((first+i)*mul) % (text_len-len). */
+int sb_generate_blocks_device(const uint8_t* d_text, uint64_t text_len, uint8_t* d_out, uint64_t stride,
+                              uint32_t len, uint64_t first, uint64_t count, uint64_t mul, void* stream, sb_error* err);
+const char* sb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

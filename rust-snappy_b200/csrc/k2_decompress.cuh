@@ -1,0 +1,216 @@
+// k2_decompress.cuh -- K2: batched raw Snappy decode, one stream per warp.
+//
+// Replaces reference src/decompress.rs:75-95 (Decoder::decompress), :130-148
+// (element loop), :161-228 (read_literal), :233-343 (read_copy) and the tag
+// table of build.rs:40-67, with the reference's exact error variants/payloads
+// (src/error.rs:72-180) reported per stream.
+//
+// Design (not a port of the scalar loop): a warp looks at 32 consecutive
+// compressed byte positions at once. Every lane decodes "the element that would
+// start at my byte" speculatively, the true element boundaries are recovered by
+// pointer doubling from lane 0 (which is always a true start), a warp scan of
+// the output lengths gives every element its output position, literal payload
+// bytes are scattered straight from the lanes that hold them, and copies are
+// replayed in stream order with all lanes moving bytes. Errors are taken from
+// the first true element in stream order that fails, so speculative lanes never
+// raise errors the serial decoder would not reach.
+#pragma once
+#include "common.cuh"
+
+namespace sbk {
+
+// varint header: reference src/bytes.rs:73-90 + src/decompress.rs:362-374
+// returns header length (0 = malformed) -- executed redundantly by all lanes.
+SB_DEVICE uint32_t k2_read_header(const uint8_t* in, uint32_t n, uint64_t* value) {
+    uint64_t v = 0;
+    unsigned shift = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (shift >= 64) return 0;
+        uint32_t b = in[i];
+        if (b < 0x80) { *value = v | ((uint64_t)b << shift); return i + 1; }
+        v |= (uint64_t)(b & 0x7F) << shift;
+        shift += 7;
+    }
+    return 0;
+}
+
+// Decode one raw stream with the calling warp. Returns the status code.
+SB_DEVICE uint32_t k2_decode_stream(const uint8_t* in, uint32_t n, uint8_t* dst, uint64_t cap,
+                                    sb_error* st, uint32_t* out_len) {
+    const unsigned lane = lane_id();
+    if (n == 0) { if (lane == 0) set_status(st, SB_EMPTY, 0, 0, 0); return SB_EMPTY; }
+    uint64_t dn64 = 0;
+    const uint32_t hl = k2_read_header(in, n, &dn64);
+    if (hl == 0) { if (lane == 0) set_status(st, SB_HEADER, 0, 0, 0); return SB_HEADER; }
+    if (dn64 > kMaxInput) { if (lane == 0) set_status(st, SB_TOO_BIG, dn64, kMaxInput, 0); return SB_TOO_BIG; }
+    if (dn64 > cap) { if (lane == 0) set_status(st, SB_BUFFER_TOO_SMALL, cap, dn64, 0); return SB_BUFFER_TOO_SMALL; }
+
+    const uint8_t* src = in + hl;
+    const uint8_t* in_end = in + n;
+    const uint64_t sn = n - hl, dn = dn64;
+    uint64_t s = 0, d = 0;
+
+    while (s < sn) {
+        // ---- fetch 40 bytes starting at the 4-byte-aligned address below src+s
+        const uintptr_t A = (uintptr_t)(src + s);
+        const unsigned mis = (unsigned)(A & 3u);
+        uint32_t word = 0;
+        if (lane < 10) {
+            const uint8_t* wp = (const uint8_t*)(A - mis) + 4 * lane;
+            if (wp >= in && wp + 4 <= in_end) {
+                word = *(const uint32_t*)wp;
+            } else {
+                for (int k = 0; k < 4; k++)
+                    if (wp + k >= in && wp + k < in_end) word |= (uint32_t)wp[k] << (8 * k);
+            }
+        }
+        const unsigned bi = mis + lane;
+        const uint32_t lo = shfl(word, bi >> 2), hi = shfl(word, (bi >> 2) + 1);
+        const unsigned sh = (bi & 3u) * 8;
+        const uint32_t tag = funnel_r(lo, hi, sh) & 0xFFu;          // byte at s+lane
+        const uint32_t next4 = sh == 24 ? hi : funnel_r(lo, hi, sh + 8);  // 4 bytes after it
+        const uint64_t rem = sn - s;                                 // bytes left from window start
+        const bool valid = lane < rem;
+
+        // ---- speculative element decode (tag layout: build.rs:40-67)
+        const unsigned kind = tag & 3u;
+        unsigned hdr;       // tag byte + trailer bytes
+        uint64_t len;       // output bytes produced
+        uint32_t off = 0;
+        if (kind == 0) {
+            const unsigned L = tag >> 2;
+            if (L < 60) { hdr = 1; len = L + 1; }
+            else {
+                const unsigned nb = L - 59;
+                hdr = 1 + nb;
+                len = (uint64_t)(nb == 4 ? next4 : (next4 & ((1u << (8 * nb)) - 1))) + 1;
+            }
+        } else if (kind == 1) {
+            hdr = 2; len = 4 + ((tag >> 2) & 7u); off = ((tag >> 5) << 8) | (next4 & 0xFFu);
+        } else if (kind == 2) {
+            hdr = 3; len = 1 + (tag >> 2); off = next4 & 0xFFFFu;
+        } else {
+            hdr = 5; len = 1 + (tag >> 2); off = next4;
+        }
+        // a literal whose payload does not end inside this window ("spill") closes the window
+        const bool spill = valid && kind == 0 && (uint64_t)lane + hdr + len > 32;
+        uint32_t E = !valid ? 64u : spill ? 64u : (uint32_t)(lane + hdr + (kind == 0 ? (uint32_t)len : 0u));
+
+        // ---- true element starts: pointer doubling from every lane, read lane 0
+        uint32_t M = 1u << lane;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            const uint32_t M2 = shfl(M, E & 31u), E2 = shfl(E, E & 31u);
+            if (E < 32) { M |= M2; E = E2; }
+        }
+        M = shfl(M, 0);
+        const bool is_start = ((M >> lane) & 1u) && valid;
+        const unsigned last = 31 - clz(M);
+
+        // ---- output position of every true element (spilling literal counts 0 here)
+        uint32_t olen = (is_start && !spill) ? (uint32_t)len : 0u;
+        uint32_t incl = olen;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const uint32_t t = shfl_up(incl, k);
+            if (lane >= (unsigned)k) incl += t;
+        }
+        const uint32_t opos = incl - olen;
+        const uint32_t win_out = shfl(incl, 31);
+        const uint64_t de = d + opos;        // output position of my element
+        const uint64_t sa = s + lane + 1;    // stream position just after my tag byte
+
+        // ---- error conditions in the reference's order of checks
+        uint32_t ecode = 0; uint64_t ea = 0, eb = 0, ec = 0;
+        if (is_start) {
+            if (kind == 0) {
+                uint64_t sp = sa;
+                if ((tag >> 2) >= 60) {
+                    if (sa + 4 > sn) { ecode = SB_LITERAL; ea = 4; eb = sn - sa; ec = dn - de; }  // :192-198
+                    sp = sa + (hdr - 1);
+                }
+                if (!ecode && (sn - sp < len || dn - de < len)) {                                   // :209-217
+                    ecode = SB_LITERAL; ea = len; eb = sn - sp; ec = dn - de;
+                }
+            } else {
+                const unsigned nb = hdr - 1;
+                if (sa + 4 > sn) {                                                                  // :439-472
+                    if (nb == 1) { if (sa >= sn) { ecode = SB_COPY_READ; ea = 1; eb = sn - sa; } }
+                    else if (nb == 2) { if (sa + 1 >= sn) { ecode = SB_COPY_READ; ea = 2; eb = sn - sa; } }
+                    else { ecode = SB_COPY_READ; ea = 4; eb = sn - sa; }
+                }
+                if (!ecode && (off == 0 || de < off)) { ecode = SB_OFFSET; ea = off; eb = de; }     // :245-250
+                if (!ecode && de + len > dn) { ecode = SB_COPY_WRITE; ea = len; eb = dn - de; }     // :328-333
+            }
+        }
+        const uint32_t emask = ballot(ecode != 0);
+        if (emask) {
+            const unsigned first = ffs(emask) - 1;
+            if (lane == first) set_status(st, ecode, ea, eb, ec);
+            return shfl(ecode, first);
+        }
+
+        // ---- literal payload bytes that sit inside the window: lane -> output byte
+        {
+            const unsigned own = 31 - clz(M & (0xFFFFFFFFu >> (31 - lane)));  // nearest start <= lane
+            const uint32_t pk = shfl((opos << 8) | (hdr << 4) | (kind << 1) | (spill ? 1u : 0u), own);
+            const unsigned ohdr = (pk >> 4) & 0xFu;
+            if (valid && (pk & 7u) == 0 && lane >= own + ohdr)
+                dst[d + (pk >> 8) + (lane - own - ohdr)] = (uint8_t)tag;
+        }
+        syncwarp();
+
+        // ---- copies, replayed in stream order; all lanes move bytes
+        uint32_t cm = ballot(is_start && kind != 0);
+        while (cm) {
+            const unsigned j = ffs(cm) - 1;
+            cm &= cm - 1;
+            const uint32_t pk = shfl((opos << 8) | (uint32_t)len, j);
+            const uint32_t coff = shfl(off, j);
+            const uint32_t clen = pk & 0xFFu;
+            uint8_t* out = dst + d + (pk >> 8);
+            const uint8_t* from = out - coff;
+            if (coff >= clen) {
+                for (uint32_t k = lane; k < clen; k += 32) out[k] = from[k];
+            } else {
+                // overlapping copy = periodic pattern of the last `coff` bytes (:306-317)
+                for (uint32_t k = lane; k < clen; k += 32) out[k] = from[k % coff];
+            }
+            syncwarp();
+        }
+
+        // ---- window advance (+ the spilling literal, copied cooperatively)
+        const uint32_t lpk = shfl((uint32_t)(spill ? 1u : 0u) | (hdr << 1), last);
+        if (lpk & 1u) {
+            const uint32_t llen = shfl((uint32_t)len, last);   // validated above: fits in 32 bits
+            const uint64_t lsrc = s + last + (lpk >> 1);
+            warp_copy(dst + d + win_out, src + lsrc, llen);
+            syncwarp();
+            s = lsrc + llen;
+            d += (uint64_t)win_out + llen;
+        } else {
+            s += shfl(E, 0);
+            d += win_out;
+        }
+    }
+    if (d != dn) {                                                                                   // :141-146
+        if (lane == 0) set_status(st, SB_HEADER_MISMATCH, dn, d, 0);
+        return SB_HEADER_MISMATCH;
+    }
+    if (lane == 0) { set_status(st, SB_OK, 0, 0, 0); if (out_len) *out_len = (uint32_t)dn; }
+    return SB_OK;
+}
+
+// Kernel body: warp w of the grid decodes units w, w+nwarps, ...
+SB_DEVICE void k2_decompress_body(const BatchDesc& b) {
+    const unsigned warps_per_block = block_dim() >> 5;
+    const uint64_t nwarps = (uint64_t)grid_dim() * warps_per_block;
+    for (uint64_t u = (uint64_t)block_idx() * warps_per_block + warp_id(); u < b.count; u += nwarps) {
+        const uint32_t i = (uint32_t)u;
+        if (b.out_lens && lane_id() == 0) b.out_lens[i] = 0;
+        k2_decode_stream(unit_in(b, i), unit_in_len(b, i), unit_out(b, i), unit_out_cap(b, i),
+                         b.statuses ? &b.statuses[i] : nullptr, b.out_lens ? &b.out_lens[i] : nullptr);
+    }
+}
+
+}  // namespace sbk

@@ -1,0 +1,71 @@
+// simt.h -- thin portability layer for the kernel bodies.
+//
+// Under nvcc the wrappers are the sm_100a intrinsics, nothing more. Under
+// -DSB_EMU (tests/emu only) the same kernel bodies are compiled by g++ against a
+// fiber-based warp emulator so their LOGIC can be checked on a machine without a
+// GPU. The emulator is test tooling: the product library is only ever built
+// from the __CUDACC__ branch and has no CPU execution path.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(SB_EMU)
+#include "../../tests/emu/simt_emu.h"
+#else
+
+#include <cuda_runtime.h>
+
+#define SB_DEVICE __device__ __forceinline__
+#define SB_DEVICE_NOINLINE __device__ __noinline__
+#define SB_FULL 0xFFFFFFFFu
+
+namespace sbk {
+
+SB_DEVICE unsigned lane_id() { return threadIdx.x & 31u; }
+SB_DEVICE unsigned warp_id() { return threadIdx.x >> 5; }
+SB_DEVICE unsigned thread_idx() { return threadIdx.x; }
+SB_DEVICE unsigned block_dim() { return blockDim.x; }
+SB_DEVICE unsigned block_idx() { return blockIdx.x; }
+SB_DEVICE unsigned grid_dim() { return gridDim.x; }
+
+SB_DEVICE uint32_t shfl(uint32_t v, unsigned src) { return __shfl_sync(SB_FULL, v, src); }
+SB_DEVICE int shfl(int v, unsigned src) { return __shfl_sync(SB_FULL, v, src); }
+SB_DEVICE uint64_t shfl(uint64_t v, unsigned src) { return __shfl_sync(SB_FULL, v, src); }
+SB_DEVICE uint32_t shfl_up(uint32_t v, unsigned d) { return __shfl_up_sync(SB_FULL, v, d); }
+SB_DEVICE uint32_t shfl_down(uint32_t v, unsigned d) { return __shfl_down_sync(SB_FULL, v, d); }
+SB_DEVICE uint32_t shfl_xor(uint32_t v, unsigned m) { return __shfl_xor_sync(SB_FULL, v, m); }
+SB_DEVICE uint32_t ballot(bool p) { return __ballot_sync(SB_FULL, p); }
+SB_DEVICE bool any(bool p) { return __any_sync(SB_FULL, p); }
+SB_DEVICE bool all(bool p) { return __all_sync(SB_FULL, p); }
+SB_DEVICE uint32_t match_any(uint32_t v) { return __match_any_sync(SB_FULL, v); }
+SB_DEVICE void syncwarp() { __syncwarp(); }
+SB_DEVICE void syncthreads() { __syncthreads(); }
+// named barrier over `nthreads` threads (multiple of 32), id in [1,15]
+SB_DEVICE void bar_sync(unsigned id, unsigned nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+SB_DEVICE int popc(uint32_t v) { return __popc(v); }
+SB_DEVICE int ffs(uint32_t v) { return __ffs(v); }          // 1-based, 0 if none
+SB_DEVICE int clz(uint32_t v) { return __clz(v); }
+SB_DEVICE int ffsll(uint64_t v) { return __ffsll((long long)v); }
+SB_DEVICE uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
+SB_DEVICE uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+
+SB_DEVICE uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+SB_DEVICE unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+SB_DEVICE uint32_t atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
+SB_DEVICE void threadfence() { __threadfence(); }
+
+// read-only / streaming global accessors
+SB_DEVICE uint32_t ldg32(const void* p) { return __ldg((const uint32_t*)p); }
+SB_DEVICE uint4 ldg128(const void* p) { return __ldg((const uint4*)p); }
+SB_DEVICE uint8_t ldg8(const void* p) { return __ldg((const uint8_t*)p); }
+// streaming (evict-first) 16-byte store for write-once output
+SB_DEVICE void stcs128(void* p, uint4 v) { __stcs((uint4*)p, v); }
+
+extern __shared__ __align__(128) unsigned char sb_dyn_smem[];
+SB_DEVICE unsigned char* smem() { return sb_dyn_smem; }
+
+}  // namespace sbk
+#endif

@@ -1,0 +1,107 @@
+"""ctypes access to the CPU warp-emulator build of the kernel bodies (TEST TOOLING)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "emu", "_build", "libemu_kernels.so")
+
+
+class SbError(C.Structure):
+    _fields_ = [("code", C.c_uint32), ("_pad", C.c_uint32), ("a", C.c_uint64), ("b", C.c_uint64), ("c", C.c_uint64)]
+
+
+class SbBatch(C.Structure):
+    _fields_ = [
+        ("in_ptrs", C.c_void_p), ("in_base", C.c_void_p), ("in_stride", C.c_uint64),
+        ("in_lens", C.c_void_p), ("in_len_uniform", C.c_uint32),
+        ("out_ptrs", C.c_void_p), ("out_base", C.c_void_p), ("out_stride", C.c_uint64),
+        ("out_caps", C.c_void_p), ("out_cap_uniform", C.c_uint32),
+        ("out_lens", C.c_void_p), ("statuses", C.c_void_p), ("count", C.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        srcs = [os.path.join(HERE, "emu", f) for f in ("emu_kernels.cpp", "simt_emu.cpp", "simt_emu.h")]
+        csrc = os.path.join(os.path.dirname(HERE), "rust-snappy_b200", "csrc")
+        srcs += [os.path.join(csrc, f) for f in os.listdir(csrc)]
+        if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(s) for s in srcs):
+            subprocess.check_call([os.path.join(HERE, "emu", "build.sh")])
+        _lib = C.CDLL(SO)
+    return _lib
+
+
+ERR = {0: "Ok", 1: "TooBig", 2: "BufferTooSmall", 3: "Empty", 4: "Header", 5: "HeaderMismatch", 6: "Literal",
+       7: "CopyRead", 8: "CopyWrite", 9: "Offset"}
+
+
+def _pack(chunks, slack=64):
+    """Concatenate byte strings into one numpy buffer with per-unit offsets."""
+    offs, at = [], 0
+    for c in chunks:
+        offs.append(at)
+        at += len(c) + slack
+    buf = np.zeros(max(at, 1), dtype=np.uint8)
+    for o, c in zip(offs, chunks):
+        buf[o:o + len(c)] = np.frombuffer(c, dtype=np.uint8)
+    return buf, offs
+
+
+def compress_units(units, with_header=True, grid=1):
+    """Run the K1 kernel body under the emulator over independent units (<=64KB each)."""
+    inbuf, inoffs = _pack(units, slack=3)
+    stride = 76544
+    out = np.full(stride * len(units) + 64, 0xEE, dtype=np.uint8)
+    lens = np.array([len(u) for u in units], dtype=np.uint32)
+    in_ptrs = np.array([inbuf.ctypes.data + o for o in inoffs], dtype=np.uint64)
+    out_lens = np.zeros(len(units), dtype=np.uint32)
+    b = SbBatch()
+    b.in_ptrs = in_ptrs.ctypes.data
+    b.in_lens = lens.ctypes.data
+    b.out_base = out.ctypes.data
+    b.out_stride = stride
+    b.out_cap_uniform = stride
+    b.out_lens = out_lens.ctypes.data
+    b.count = len(units)
+    lib().emu_compress_batch(C.byref(b), 1 if with_header else 0, grid)
+    return [bytes(out[i * stride:i * stride + int(out_lens[i])]) for i in range(len(units))]
+
+
+def decompress_units(streams, caps, grid=1, block=32):
+    """Run the K2 kernel body under the emulator. Returns [(status tuple, bytes)]."""
+    inbuf, inoffs = _pack(streams, slack=0)
+    ocap = [max(c, 0) for c in caps]
+    ooffs, at = [], 0
+    for c in ocap:
+        ooffs.append(at)
+        at += c + 16
+    out = np.full(at + 16, 0xEE, dtype=np.uint8)
+    lens = np.array([len(s) for s in streams], dtype=np.uint32)
+    in_ptrs = np.array([inbuf.ctypes.data + o for o in inoffs], dtype=np.uint64)
+    out_ptrs = np.array([out.ctypes.data + o for o in ooffs], dtype=np.uint64)
+    out_caps = np.array(ocap, dtype=np.uint32)
+    out_lens = np.zeros(len(streams), dtype=np.uint32)
+    st = (SbError * len(streams))()
+    b = SbBatch()
+    b.in_ptrs = in_ptrs.ctypes.data
+    b.in_lens = lens.ctypes.data
+    b.out_ptrs = out_ptrs.ctypes.data
+    b.out_caps = out_caps.ctypes.data
+    b.out_lens = out_lens.ctypes.data
+    b.statuses = C.addressof(st)
+    b.count = len(streams)
+    lib().emu_decompress_batch(C.byref(b), grid, block)
+    res = []
+    for i in range(len(streams)):
+        e = st[i]
+        res.append(((ERR.get(e.code, str(e.code)), e.a, e.b, e.c),
+                    bytes(out[ooffs[i]:ooffs[i] + int(out_lens[i])]),
+                    bytes(out[ooffs[i] + ocap[i]:ooffs[i] + ocap[i] + 16])))
+    return res

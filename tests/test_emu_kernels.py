@@ -1,0 +1,75 @@
+"""Kernel LOGIC checks on CPU: the CUDA kernel bodies (rust-snappy_b200/csrc/*.cuh)
+compiled by g++ against the fiber warp emulator in tests/emu, compared with the
+oracle. This is test tooling for GPU-less development -- the product library is
+never built this way."""
+import random
+
+import pytest
+
+import emu_helpers as emu
+from conftest import corpus
+from kats import COPY_CLOSE_TO_END, DECODE_ERRORS, RANDOM, small_copy_inputs, small_regular_inputs
+
+
+def blocks_of(data):
+    return [data[i:i + 65536] for i in range(0, len(data), 65536)]
+
+
+@pytest.mark.parametrize("name", ["html", "urls.10K", "fireworks.jpeg", "paper-100k.pdf", "alice29.txt",
+                                  "geo.protodata", "kppkn.gtb", "Mark.Twain-Tom.Sawyer.txt"])
+def test_k1_k2_corpus_blocks(oracle, name):
+    blocks = blocks_of(corpus(name))[:3]
+    want = [oracle.compress(b) for b in blocks]
+    assert emu.compress_units(blocks, grid=2) == want
+    for (st, out, guard), b in zip(emu.decompress_units(want, [len(b) for b in blocks], grid=2, block=64), blocks):
+        assert st[0] == "Ok" and out == b and guard == b"\xee" * 16
+
+
+def test_k1_small_inputs(oracle):
+    units = [b"", b"\x00"] + RANDOM + small_copy_inputs() + small_regular_inputs()[::9]
+    assert emu.compress_units(units) == [oracle.compress(u) for u in units]
+
+
+def test_k2_error_kats():
+    kats = [k for k in DECODE_ERRORS]
+    res = emu.decompress_units([k[1] for k in kats], [1024 if k[3] else 64 for k in kats])
+    for k, (st, _, guard) in zip(kats, res):
+        if k[3] or k[0] == "err_empty":
+            assert st == k[2]
+        assert guard == b"\xee" * 16
+    # non-header KATs decode into exactly decompress_len bytes
+    from oracle import oracle as o
+    body = [k for k in kats if not k[3] and k[1]]
+    res = emu.decompress_units([k[1] for k in body], [o.decompress_len(k[1]) for k in body])
+    for k, (st, _, guard) in zip(body, res):
+        assert st == k[2], k[0]
+        assert guard == b"\xee" * 16
+    for stream, want in COPY_CLOSE_TO_END:
+        (st, out, guard), = emu.decompress_units([stream], [len(want)])
+        assert st[0] == "Ok" and out == want and guard == b"\xee" * 16
+
+
+def test_k2_fuzz_against_oracle(oracle):
+    from oracle.oracle import OracleError
+    rng = random.Random(11)
+    base = oracle.compress(corpus("alice29.txt")[:6000])
+    streams, caps = [], []
+    for _ in range(150):
+        s = bytearray(base)
+        for _ in range(rng.randrange(1, 4)):
+            s[rng.randrange(len(s))] ^= 1 << rng.randrange(8)
+        if rng.random() < 0.3:
+            s = s[:rng.randrange(1, len(s))]
+        s = bytes(s)
+        try:
+            cap = min(oracle.decompress_len(s), 1 << 18)
+        except OracleError:
+            cap = 512
+        streams.append(s); caps.append(cap)
+    for s, cap, (st, out, guard) in zip(streams, caps, emu.decompress_units(streams, caps, block=128)):
+        try:
+            want = (("Ok", 0, 0, 0), oracle.decompress(s, cap=cap))
+        except OracleError as e:
+            want = (e.err, b"")
+        assert (st, out if st[0] == "Ok" else b"") == want
+        assert guard == b"\xee" * 16

@@ -1,0 +1,296 @@
+"""CUDA path vs the oracle, through the C ABI (python -m pytest -m gpu).
+
+Mirrors the reference's test/tests.rs: round trips on the corpus (raw + frame),
+the golden encoder vector, decoder KATs with exact error payloads, the small
+input sweeps, property round trips, and the frame encoder equivalences.
+"""
+import io
+import random
+
+import pytest
+
+from conftest import CORPUS, corpus
+from kats import (COPY_CLOSE_TO_END, DECODE_ERRORS, RANDOM, small_copy_inputs, small_regular_inputs)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def snap():
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    import gpu_helpers
+    return gpu_helpers.snap()
+
+
+def press(snap, d):
+    return snap.raw.Encoder().compress_vec(d)
+
+
+def depress(snap, d):
+    return snap.raw.Decoder().decompress_vec(d)
+
+
+def test_golden_rev(snap, oracle):
+    # test/tests.rs:199-205
+    gold = corpus("Mark.Twain-Tom.Sawyer.txt.rawsnappy")
+    assert press(snap, depress(snap, gold)) == gold
+
+
+@pytest.mark.parametrize("name", CORPUS)
+def test_corpus_raw_bit_exact_and_roundtrip(snap, oracle, name):
+    # testtrip!(data_*): roundtrip_raw + compressed bytes equal to the reference encoder (oracle)
+    data = corpus(name)
+    c = press(snap, data)
+    assert c == oracle.compress(data)
+    assert depress(snap, c) == data
+
+
+@pytest.mark.parametrize("name", CORPUS)
+def test_corpus_frame(snap, oracle, name):
+    # roundtrip_frame + read_and_write_frame_encoder_match (test/tests.rs:75-88)
+    data = corpus(name)
+    w = snap.write.FrameEncoder(io.BytesIO())
+    w.write_all(data)
+    written = w.into_inner().getvalue()
+    assert written == oracle.frame_encode(data)
+    assert snap.read.FrameEncoder(io.BytesIO(data)).read_to_end() == written
+    assert snap.frame.decode_all(written) == data
+    if len(data) <= 200000:
+        assert snap.read.FrameDecoder(io.BytesIO(written)).read_to_end() == data
+
+
+def test_config1_html_single_block(snap, oracle):
+    # BASELINE.json configs[0]: data/html, one 64KB block and the whole (2-block) file
+    html = corpus("html")
+    for d in (html[:65536], html):
+        c = press(snap, d)
+        assert c == oracle.compress(d)
+        assert depress(snap, c) == d
+    assert len(press(snap, html)) == 22843 and len(press(snap, html[:65536])) == 16533
+
+
+@pytest.mark.parametrize("name,data,want,bad_header", DECODE_ERRORS, ids=[k[0] for k in DECODE_ERRORS])
+def test_decode_error_kats(snap, name, data, want, bad_header):
+    import gpu_helpers
+    if bad_header:
+        with pytest.raises(snap.Error) as ei:
+            snap.raw.decompress_len(data)
+        assert ei.value.as_tuple() == want
+        cap = 1024
+    else:
+        cap = snap.raw.decompress_len(data)
+    with pytest.raises(snap.Error) as ei:
+        snap.raw.Decoder().decompress(data, bytearray(cap))
+    assert ei.value.as_tuple() == want
+    # the batched kernel path reports the same status
+    if data:
+        (st, _), = gpu_helpers.decompress_batch_host([data], [cap])
+        assert st == want
+
+
+@pytest.mark.parametrize("stream,want", COPY_CLOSE_TO_END)
+def test_copy_close_to_end(snap, stream, want):
+    assert depress(snap, stream) == want
+
+
+def test_empty_and_tiny(snap, oracle):
+    assert press(snap, b"") == b"\x00"
+    assert depress(snap, b"\x00") == b""
+    assert press(snap, b"\x00") == oracle.compress(b"\x00")
+    w = snap.write.FrameEncoder(io.BytesIO())
+    w.write_all(b"")
+    assert w.into_inner().getvalue() == b""                      # src/write.rs:155-157
+    assert snap.frame.decode_all(b"") == b""
+    with pytest.raises(snap.Error) as ei:
+        snap.raw.Encoder().compress(b"abc", bytearray(10))
+    assert ei.value.as_tuple() == ("BufferTooSmall", 10, 35, 0)   # src/compress.rs:111-116
+
+
+def test_small_sweeps_batched(snap, oracle):
+    import gpu_helpers
+    units = RANDOM + small_copy_inputs() + small_regular_inputs()
+    got = gpu_helpers.compress_batch_host(units)
+    for u, g in zip(units, got):
+        assert g == oracle.compress(u)
+    back = gpu_helpers.decompress_batch_host(got, [len(u) for u in units])
+    for u, (st, b) in zip(units, back):
+        assert st[0] == "Ok" and b == u
+
+
+def test_property_roundtrip(snap, oracle):
+    import gpu_helpers
+    import pyarrow as pa
+    rng = random.Random(99)
+    units = []
+    for _ in range(400):
+        n = rng.randrange(0, 10000)
+        alpha = rng.choice([2, 3, 16, 256])
+        units.append(bytes(rng.randrange(alpha) for _ in range(n)))
+    got = gpu_helpers.compress_batch_host(units)
+    assert all(g == oracle.compress(u) for u, g in zip(units, got))
+    back = gpu_helpers.decompress_batch_host(got, [len(u) for u in units])
+    assert all(st[0] == "Ok" and b == u for u, (st, b) in zip(units, back))
+    # streams from another encoder (Google C++ snappy via pyarrow) decode to the same bytes
+    codec = pa.Codec("snappy")
+    foreign = [codec.compress(u).to_pybytes() for u in units if u]
+    back = gpu_helpers.decompress_batch_host(foreign, [len(u) for u in units if u])
+    assert all(st[0] == "Ok" and b == u for u, (st, b) in zip([u for u in units if u], back))
+
+
+def test_corrupt_streams_match_oracle(snap, oracle):
+    """Bit-flipped / truncated streams: identical status (variant + payload) or identical output."""
+    import gpu_helpers
+    from oracle.oracle import OracleError
+    rng = random.Random(5)
+    base = oracle.compress(corpus("alice29.txt")[:20000])
+    streams = []
+    for _ in range(300):
+        s = bytearray(base)
+        for _ in range(rng.randrange(1, 4)):
+            s[rng.randrange(len(s))] ^= 1 << rng.randrange(8)
+        if rng.random() < 0.3:
+            s = s[:rng.randrange(1, len(s))]
+        streams.append(bytes(s))
+    for i in (1, 2, 3):
+        streams.append(corpus("baddata%d.snappy" % i))
+    caps = []
+    for s in streams:
+        try:
+            caps.append(min(oracle.decompress_len(s), 1 << 20))
+        except OracleError:
+            caps.append(1024)
+    got = gpu_helpers.decompress_batch_host(streams, caps)
+    for s, cap, (st, out) in zip(streams, caps, got):
+        try:
+            want = (("Ok", 0, 0, 0), oracle.decompress(s, cap=cap))
+        except OracleError as e:
+            want = (e.err, b"")
+        assert (st, out) == want
+
+
+def test_foreign_tag_forms(snap, oracle):
+    """copy-4 tags and 3/4-byte literal lengths (never emitted by the encoder; build.rs:61-64)."""
+    lit = bytes(range(256)) * 2
+    streams = [
+        bytes([0x80, 0x04]) + bytes([62 << 2, 0xFF, 0x01, 0x00]) + lit,                      # 3-byte literal length
+        bytes([0x80, 0x04]) + bytes([63 << 2, 0xFF, 0x01, 0x00, 0x00]) + lit,                # 4-byte literal length
+        bytes([0x88, 0x04]) + bytes([61 << 2, 0xFF, 0x01]) + lit + bytes([(7 << 2) | 3, 0x00, 0x02, 0x00, 0x00]),  # copy4
+    ]
+    for s in streams:
+        assert depress(snap, s) == oracle.decompress(s)
+
+
+def test_crc32c(snap, oracle):
+    rng = random.Random(3)
+    for n in [0, 1, 3, 4, 5, 63, 64, 65, 127, 1000, 4097, 65535, 65536, 100000]:
+        d = bytes(rng.randrange(256) for _ in range(n))
+        assert snap.raw.crc32c_masked(d) == oracle.crc32c_masked(d)
+
+
+def test_frame_decoder_errors(snap, oracle):
+    import gpu_helpers
+    from oracle.oracle import OracleError
+    ident = b"\xff\x06\x00\x00sNaPpY"
+    good = oracle.frame_encode(b"hello world, hello world, hello world")
+    bad = bytearray(good); bad[14] ^= 1
+    pdf = oracle.frame_encode(corpus("paper-100k.pdf"))
+    late = bytearray(pdf); late[-5] ^= 0x40
+    streams = [
+        b"123", b"\x00\x04\x00\x00abcd", ident + b"\x02\x00\x00\x00", b"\xff\x05\x00\x00sNaPp",
+        b"\xff\x06\x00\x00sNaPpZ", ident + b"\x00\xff\xff\xff", ident + b"\x01\x03\x00\x00abc", bytes(bad),
+        ident + b"\x80\x03\x00\x00xyz" + b"\xfe\x02\x00\x00\x00\x00" + ident + good[10:],
+        good + b"\x00\x07", good[:-3], bytes(late), ident + b"\x00\x04\x00\x00\x00\x00\x00\x00",
+        ident + b"\x00\x05\x00\x00\x00\x00\x00\x00\x80",
+    ]
+    for s in streams:
+        try:
+            want = ("Ok", oracle.frame_decode(s))
+        except OracleError as e:
+            want = (e.err, None)
+        for impl in (snap.frame.decode_all, lambda x: snap.read.FrameDecoder(io.BytesIO(x)).read_to_end()):
+            try:
+                got = ("Ok", impl(s))
+            except Exception as e:  # noqa: BLE001
+                got = (gpu_helpers.err_tuple(e), None)
+            assert got == want, (s[:24], got, want)
+
+
+def test_write_frame_encoder_buffering(snap, oracle):
+    """Chunk boundaries follow the reference's staging rules (src/write.rs:123-161)."""
+    data = corpus("html_x_4")[:250000]
+    for pieces in ([100000, 100000, 50000], [1, 65535, 70000, 114464], [65536, 65536, 65536, 53392], [30000] * 8 + [10000]):
+        w = snap.write.FrameEncoder(io.BytesIO())
+        at, src, model = 0, b"", [b"\xff\x06\x00\x00sNaPpY"]
+
+        def inner(buf):
+            for i in range(0, len(buf), 65536):
+                model.append(oracle.compress_frame(buf[i:i + 65536]))
+        for p in pieces:
+            buf = data[at:at + p]; at += p
+            w.write(buf)
+            while True:                       # model of src/write.rs:123-152
+                free = 65536 - len(src)
+                if len(buf) <= free:
+                    break
+                if not src:
+                    inner(buf); buf = b""
+                else:
+                    src += buf[:free]; inner(src); src = b""; buf = buf[free:]
+            src += buf
+        if src:
+            inner(src)
+        assert w.into_inner().getvalue() == b"".join(model)
+        assert snap.frame.decode_all(b"".join(model)) == data[:at]
+
+
+def test_read_frame_encoder_big_and_little_buffers(snap):
+    # test/tests.rs:321-340
+    data = corpus("html")
+    big = snap.read.FrameEncoder(io.BytesIO(data)).read_to_end()
+    r = snap.read.FrameEncoder(io.BytesIO(data))
+    little = bytearray()
+    while True:
+        p = r.read(5)
+        if not p:
+            break
+        little += p
+    assert bytes(little) == big
+
+
+def test_device_batch_api_full_size_blocks(snap, oracle):
+    """Device-resident batch (the measured path): 64KB text blocks generated on device,
+    compressed, compared with the oracle, decompressed and compared with the input."""
+    import ctypes as C
+    import torch
+    import gpu_helpers
+    L = gpu_helpers.lib()
+    text = b"".join(corpus(n) for n in ("alice29.txt", "asyoulik.txt", "lcet10.txt", "plrabn12.txt"))
+    count, blk, stride, mul = 3000, 65536, 76544, 65521
+    dev = torch.device("cuda:0")
+    t_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).to(dev)
+    t_in = torch.empty(count * blk, dtype=torch.uint8, device=dev)
+    t_c = torch.empty(count * stride, dtype=torch.uint8, device=dev)
+    t_out = torch.zeros(count * blk, dtype=torch.uint8, device=dev)
+    t_clen = torch.zeros(count, dtype=torch.int32, device=dev)
+    t_dlen = torch.zeros(count, dtype=torch.int32, device=dev)
+    t_st = torch.zeros(count * 4, dtype=torch.int64, device=dev)
+    e = snap._lib.SbError()
+    st = torch.cuda.current_stream().cuda_stream
+    assert L.sb_generate_blocks_device(t_text.data_ptr(), len(text), t_in.data_ptr(), blk, blk, 0, count, mul, st, C.byref(e)) == 0
+    b = gpu_helpers.batch_from_tensors(t_in, blk, blk, t_c, stride, stride, t_clen, None, count)
+    assert L.sb_compress_batch_device(C.byref(b), st, C.byref(e)) == 0
+    b2 = gpu_helpers.batch_from_tensors(t_c, stride, 0, t_out, blk, blk, t_dlen, t_st, count, in_lens_t=t_clen)
+    assert L.sb_decompress_batch_device(C.byref(b2), st, C.byref(e)) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(t_in, t_out)
+    assert int(t_st.view(count, 4)[:, 0].abs().sum()) == 0
+    assert bool((t_dlen == blk).all())
+    clen = t_clen.cpu().numpy()
+    c_host = t_c.cpu().numpy()
+    span = len(text) - blk
+    for i in list(range(0, count, 97)) + [count - 1]:
+        off = (i * mul) % span
+        want = oracle.compress(text[off:off + blk])
+        assert bytes(c_host[i * stride:i * stride + int(clen[i])]) == want
