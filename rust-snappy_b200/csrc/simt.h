@@ -56,6 +56,14 @@ SB_DEVICE uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v);
 SB_DEVICE unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 SB_DEVICE uint32_t atomic_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 SB_DEVICE void threadfence() { __threadfence(); }
+SB_DEVICE void threadfence_block() { __threadfence_block(); }
+SB_DEVICE uint32_t reduce_or(uint32_t v) { return __reduce_or_sync(SB_FULL, v); }
+SB_DEVICE uint32_t reduce_add(uint32_t v) { return __reduce_add_sync(SB_FULL, v); }
+SB_DEVICE uint32_t reduce_max(uint32_t v) { return __reduce_max_sync(SB_FULL, v); }
+// polite spin-wait hint inside producer/consumer polling loops
+SB_DEVICE void spin() { __nanosleep(32); }
+SB_DEVICE uint32_t ld_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+SB_DEVICE void st_volatile(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
 
 // read-only / streaming global accessors
 SB_DEVICE uint32_t ldg32(const void* p) { return __ldg((const uint32_t*)p); }

@@ -20,7 +20,7 @@
 namespace {
 
 // ------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(32) k1_compress_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body(b, flags); }
+__global__ void __launch_bounds__(64) k1_compress_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body(b, flags); }
 __global__ void __launch_bounds__(128) k2_decompress_kernel(sb_batch b) { sbk::k2_decompress_body(b); }
 __global__ void __launch_bounds__(256) k3_crc_kernel(sb_batch b) { sbk::k3_crc_body(b); }
 __global__ void __launch_bounds__(256) k4_sizes_kernel(sbk::FramePlan p) { sbk::k4_sizes_body(p); }
@@ -106,7 +106,7 @@ int launch_k1(Ctx& c, const sb_batch& b, uint32_t flags, cudaStream_t st, sb_err
     if (b.count == 0) return 0;
     unsigned grid = (unsigned)(2 * c.sms);
     if (grid > b.count) grid = b.count;
-    k1_compress_kernel<<<grid, 32, sbk::K1_SMEM_BYTES, st>>>(b, flags);
+    k1_compress_kernel<<<grid, sbk::K1_THREADS, sbk::K1_SMEM_BYTES, st>>>(b, flags);
     g_launches++;
     CK(cudaGetLastError());
     return 0;

@@ -13,7 +13,7 @@ extern "C" {
 
 int emu_compress_batch(const sb_batch* b, uint32_t flags, unsigned grid) {
     K1Args a{*b, flags};
-    sbemu::launch(grid, 32, sbk::K1_SMEM_BYTES, k1_entry, &a);
+    sbemu::launch(grid, sbk::K1_THREADS, sbk::K1_SMEM_BYTES, k1_entry, &a);
     return 0;
 }
 

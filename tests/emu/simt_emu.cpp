@@ -57,15 +57,23 @@ void run_block(Block& b, void (*entry)(void*), void* arg, size_t smem_bytes) {
     }
     g_blk = &b;
     unsigned live = nthreads;
+    // SBEMU_ORDER=reverse|shuffle perturbs the lane schedule to flush out code that
+    // silently relies on lanes running in index order
+    const char* ord = getenv("SBEMU_ORDER");
+    const int mode = !ord ? 0 : (ord[0] == 'r' ? 1 : 2);
+    unsigned rng = 12345u + b.block_idx;
     while (live) {
         live = 0;
-        for (unsigned t = 0; t < nthreads; t++) {
+        for (unsigned k = 0; k < nthreads; k++) {
+            unsigned t = k;
+            if (mode == 1) t = nthreads - 1 - k;
+            else if (mode == 2) { rng = rng * 1664525u + 1013904223u; t = (k + (rng >> 16)) % nthreads; }
             Fiber& f = fibers[t];
             if (f.done) continue;
             g_cur = &f;
             sbemu_switch(&b.sched_sp, f.sp);
-            if (!f.done) live++;
         }
+        for (unsigned t = 0; t < nthreads; t++) live += fibers[t].done ? 0 : 1;
     }
     g_cur = nullptr;
     for (auto& f : fibers) free(f.stack);

@@ -159,6 +159,28 @@ SB_DEVICE uint32_t atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o
 SB_DEVICE unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 SB_DEVICE uint32_t atomic_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 SB_DEVICE void threadfence() {}
+SB_DEVICE void threadfence_block() {}
+SB_DEVICE uint32_t reduce_or(uint32_t v) {
+    const uint64_t* a = sbemu::warp_gather(v);
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) r |= (uint32_t)a[i];
+    return r;
+}
+SB_DEVICE uint32_t reduce_add(uint32_t v) {
+    const uint64_t* a = sbemu::warp_gather(v);
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) r += (uint32_t)a[i];
+    return r;
+}
+SB_DEVICE uint32_t reduce_max(uint32_t v) {
+    const uint64_t* a = sbemu::warp_gather(v);
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) if ((uint32_t)a[i] > r) r = (uint32_t)a[i];
+    return r;
+}
+SB_DEVICE void spin() { sbemu::yield(); }
+SB_DEVICE uint32_t ld_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+SB_DEVICE void st_volatile(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
 
 SB_DEVICE uint32_t ldg32(const void* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 SB_DEVICE uint4 ldg128(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }
