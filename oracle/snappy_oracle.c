@@ -233,7 +233,9 @@ int orc_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                 s += nb;
             }
             if (sn - s < len || dn - d < len) return fail(err, ORC_LITERAL, len, sn - s, dn - d);
-            memcpy(out + d, src + s, (size_t)len);
+            /* same trick as the reference (:170-186): a fixed 16-byte move when there is room */
+            if (len <= 16 && s + 16 <= sn && d + 16 <= dn) memcpy(out + d, src + s, 16);
+            else memcpy(out + d, src + s, (size_t)len);
             s += len; d += len;
         } else {
             /* src/decompress.rs:233-343 and TagEntry::offset :433-474 */
@@ -258,7 +260,15 @@ int orc_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
             s += nb;
             if (off == 0 || d < off) return fail(err, ORC_OFFSET, off, d, 0);
             if (d + len > dn) return fail(err, ORC_COPY_WRITE, len, dn - d, 0);
-            for (uint64_t i = 0; i < len; i++) out[d + i] = out[d + i - off];
+            /* output-equivalent to the byte loop; 8-byte strides when source and
+             * destination are at least 8 apart and the over-write stays inside dst
+             * (the reference does the same with 16-byte strides, :256-326) */
+            if (off >= 8 && d + len + 8 <= dn) {
+                uint8_t *q = out + d;
+                for (uint64_t i = 0; i < len; i += 8) memcpy(q + i, q + i - off, 8);
+            } else {
+                for (uint64_t i = 0; i < len; i++) out[d + i] = out[d + i - off];
+            }
             d += len;
         }
     }

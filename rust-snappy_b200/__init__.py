@@ -6,7 +6,7 @@ the C ABI of libsnapb200.so (hand-written sm_100a kernels; no CPU fallback).
     snap::read::{FrameDecoder, FrameEncoder}                       -> .read
     snap::Error                                                    -> .Error
 """
-from . import _lib, frame, raw, read, write  # noqa: F401
+from . import _lib, frame, raw, read, shard, write  # noqa: F401
 from .error import Error, NoDevice, UnexpectedEof  # noqa: F401
 
 _lib.lib()  # fail loudly at import time when the CUDA library is not built

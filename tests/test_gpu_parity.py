@@ -294,3 +294,18 @@ def test_device_batch_api_full_size_blocks(snap, oracle):
         off = (i * mul) % span
         want = oracle.compress(text[off:off + blk])
         assert bytes(c_host[i * stride:i * stride + int(clen[i])]) == want
+
+
+def test_gpu_sharded_frame_encode(snap, oracle):
+    """Two chunk ranges encoded on the device (rank 0 carries the stream identifier) concatenate
+    to the single-stream bytes; the frame decoder accepts the result."""
+    import torch
+    data = corpus("lcet10.txt")
+    t = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    parts = []
+    for rank in range(2):
+        part, _, _ = snap.shard.frame_encode_sharded(t, rank, 2)
+        parts.append(bytes(part.cpu().numpy()))
+    torch.cuda.synchronize()
+    assert b"".join(parts) == oracle.frame_encode(data)
+    assert snap.frame.decode_all(b"".join(parts)) == data
