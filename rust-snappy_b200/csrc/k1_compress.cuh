@@ -36,11 +36,15 @@ static const uint32_t K1_WIN_BYTES = 65536 + 64;             // window + slack f
 static const uint32_t K1_TABLE_BYTES = 32768;                // 16K-entry u16 table
 static const uint32_t K1_RING = 1024;                        // copy events in flight
 static const uint32_t K1_SMEM_BYTES = K1_WIN_BYTES + K1_TABLE_BYTES + K1_RING * 8 + 64;
-static const uint32_t K1_THREADS = 64;
 
+// 4 bytes at win+p through two aligned word loads. `win` may be a shared-memory window
+// (4-byte aligned) or the unit's input in global memory (any alignment): the loads are
+// aligned on the absolute address. Callers never ask for bytes past the end of the unit
+// except for the word that contains the last valid byte.
 SB_DEVICE uint32_t k1_rd32(const uint8_t* win, uint32_t p) {
-    const uint32_t* w = (const uint32_t*)(win + (p & ~3u));
-    return funnel_r(w[0], w[1], (p & 3u) * 8);
+    const uintptr_t a = (uintptr_t)(win + p);
+    const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+    return funnel_r(w[0], w[1], (unsigned)(a & 3u) * 8);
 }
 
 // ---------------------------------------------------------------- event ring
@@ -51,20 +55,38 @@ struct K1Ring {
 SB_DEVICE uint64_t k1_event(uint32_t pos, uint32_t len, uint32_t off) {
     return (uint64_t)pos | ((uint64_t)len << 17) | ((uint64_t)off << 34);
 }
-// producer side: `head` is the parser warp's private copy of ctrl[0]
-SB_DEVICE void k1_wait_space(const K1Ring& r, uint32_t head, uint32_t need) {
-    while (head + need - ld_volatile(&r.ctrl[1]) > K1_RING) spin();
-}
-SB_DEVICE void k1_publish(const K1Ring& r, uint32_t head) {
+// producer side. The parser keeps private copies of the ring counters and only
+// touches the shared ones when it has to: `tail_seen` is refreshed when the ring
+// looks full, `head` is published every K1_PUBLISH events (the emitter works on
+// fuller batches and the parser pays one fence per batch instead of one per window).
+struct K1Prod {
+    uint32_t head;        // events written so far
+    uint32_t published;   // value of ctrl[0]
+    uint32_t tail_seen;   // last value read from ctrl[1]
+};
+static const uint32_t K1_PUBLISH = 24;
+
+SB_DEVICE void k1_publish(const K1Ring& r, K1Prod& pr) {
+    if (pr.published == pr.head) return;
     threadfence_block();
     syncwarp();
-    if (lane_id() == 0) st_volatile(&r.ctrl[0], head);
+    if (lane_id() == 0) st_volatile(&r.ctrl[0], pr.head);
+    pr.published = pr.head;
 }
-SB_DEVICE void k1_push(const K1Ring& r, uint32_t& head, uint64_t e) {
-    k1_wait_space(r, head, 1);
-    if (lane_id() == 0) r.ev[head % K1_RING] = e;
-    head++;
-    k1_publish(r, head);
+SB_DEVICE void k1_wait_space(const K1Ring& r, K1Prod& pr, uint32_t need) {
+    if (pr.head + need - pr.tail_seen <= K1_RING) return;
+    k1_publish(r, pr);                                   // the emitter must see everything before we wait on it
+    for (;;) {
+        pr.tail_seen = shfl(ld_volatile(&r.ctrl[1]), 0);   // one reader: the decision must be warp-uniform
+        if (pr.head + need - pr.tail_seen <= K1_RING) return;
+        spin();
+    }
+}
+SB_DEVICE void k1_push(const K1Ring& r, K1Prod& pr, uint64_t e) {
+    k1_wait_space(r, pr, 1);
+    if (lane_id() == 0) r.ev[pr.head % K1_RING] = e;
+    pr.head++;
+    if (pr.head - pr.published >= K1_PUBLISH) k1_publish(r, pr);
 }
 
 // ------------------------------------------------------------- serial pieces
@@ -109,7 +131,7 @@ SB_DEVICE void k1_preinsert(const uint8_t* win, uint16_t* table, unsigned shift,
 // until the parse position reaches `target` or the block is finished.
 // Returns true when the block is finished.
 SB_DEVICE bool k1_serial(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
-                         K1State& st, uint32_t target, const K1Ring& ring, uint32_t& head) {
+                         K1State& st, uint32_t target, const K1Ring& ring, K1Prod& head) {
     const unsigned lane = lane_id();
     for (;;) {
         uint32_t cand;
@@ -173,33 +195,52 @@ SB_DEVICE bool k1_serial(const uint8_t* win, uint32_t n, uint16_t* table, unsign
     }
 }
 
-// One 32-position window on the fast path. Returns false (state untouched, table
-// restored) when the window must be replayed serially.
-SB_DEVICE bool k1_window(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
-                         K1State& st, const K1Ring& ring, uint32_t& head) {
-    const unsigned lane = lane_id();
-    const uint32_t w = st.s & ~31u, i0 = st.s - w, p = w + lane;
-    // ---- speculative probe of every position against the table as of the window start
-    const uint32_t* aw = (const uint32_t*)(win + (p & ~3u));
-    const unsigned ash = (p & 3u) * 8;
+// Per-lane result of probing one 32-position window against the table as it was when
+// the probe ran (possibly a little stale when several parser warps are pipelined).
+struct K1Pre {
+    uint32_t h;      // hash of this lane's position
+    uint32_t c;      // candidate read from the table
+    uint32_t L;      // match length: exact up to 11, 12 = "12 or more"
+    uint32_t E;      // ballot: a probe at lane i would hit
+    bool eq;
+};
+
+SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w) {
+    const uint32_t p = w + lane_id();
+    K1Pre r;
+    const uintptr_t aa = (uintptr_t)(win + p);
+    const uint32_t* aw = (const uint32_t*)(aa & ~(uintptr_t)3);
+    const unsigned ash = (unsigned)(aa & 3u) * 8;
     const uint32_t a0 = aw[0], a1 = aw[1], a2 = aw[2], a3 = aw[3];
     const uint32_t cur = funnel_r(a0, a1, ash);
-    const uint32_t h = K1_HASH(cur);
-    const uint32_t c = table[h];
-    const uint32_t* bw = (const uint32_t*)(win + (c & ~3u));
-    const unsigned bsh = (c & 3u) * 8;
+    r.h = K1_HASH(cur);
+    r.c = table[r.h];
+    const uintptr_t ba = (uintptr_t)(win + r.c);
+    const uint32_t* bw = (const uint32_t*)(ba & ~(uintptr_t)3);
+    const unsigned bsh = (unsigned)(ba & 3u) * 8;
     const uint32_t b0 = bw[0], b1 = bw[1], b2 = bw[2], b3 = bw[3];
-    const bool eq = cur == funnel_r(b0, b1, bsh);
-    uint32_t L = 4;                                             // match length, exact up to 11, 12 = "12 or more"
-    {
-        const uint32_t x4 = funnel_r(a1, a2, ash) ^ funnel_r(b1, b2, bsh);
-        if (x4) L += (uint32_t)(ffs(x4) - 1) >> 3;
-        else {
-            const uint32_t x8 = funnel_r(a2, a3, ash) ^ funnel_r(b2, b3, bsh);
-            L = 8 + (x8 ? (uint32_t)(ffs(x8) - 1) >> 3 : 4);
-        }
+    r.eq = cur == funnel_r(b0, b1, bsh);
+    r.L = 4;
+    const uint32_t x4 = funnel_r(a1, a2, ash) ^ funnel_r(b1, b2, bsh);
+    if (x4) r.L += (uint32_t)(ffs(x4) - 1) >> 3;
+    else {
+        const uint32_t x8 = funnel_r(a2, a3, ash) ^ funnel_r(b2, b3, bsh);
+        r.L = 8 + (x8 ? (uint32_t)(ffs(x8) - 1) >> 3 : 4);
     }
-    const uint32_t E = ballot(eq);
+    r.E = ballot(r.eq);
+    return r;
+}
+
+// Finish one window from a probe result that is known to be current for every lane
+// from the entry position on. Returns false (state untouched, table restored) when
+// the window must be replayed serially.
+SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
+                         K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre& pre) {
+    const unsigned lane = lane_id();
+    const uint32_t w = st.s & ~31u, i0 = st.s - w, p = w + lane;
+    const uint32_t h = pre.h, c = pre.c, E = pre.E;
+    const bool eq = pre.eq;
+    uint32_t L = pre.L;
     // first copy start from the entry state
     auto nextbit = [&](uint32_t x) -> uint32_t {
         if (x >= 32) return 32;
@@ -220,10 +261,10 @@ SB_DEVICE bool k1_window(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         uint32_t nx = 64;
         if (eq && e < 32) { nx = ((E >> e) & 1u) ? e : nextbit(e + 1); if (nx >= 32) nx = 64; }
         uint32_t M = 1u << lane, T = nx;
-#pragma unroll
         for (int r = 0; r < 5; r++) {
             const uint32_t M2 = shfl(M, T & 31u), T2 = shfl(T, T & 31u);
             if (T < 32) { M |= M2; T = T2; }
+            if (r >= 1 && !any(T < 32)) break;            // every chain has left the window
         }
         CS = f < 32 ? shfl(M, f) : 0;
         const uint32_t unk = CS & longmask;
@@ -262,9 +303,9 @@ SB_DEVICE bool k1_window(const uint8_t* win, uint32_t n, uint16_t* table, unsign
     const uint32_t ncopy = popc(CS);
     if (ncopy) {
         k1_wait_space(ring, head, ncopy);
-        if (taken) ring.ev[(head + popc(CS & ((1u << lane) - 1u))) % K1_RING] = k1_event(p, L, p - c);
-        head += ncopy;
-        k1_publish(ring, head);
+        if (taken) ring.ev[(head.head + popc(CS & ((1u << lane) - 1u))) % K1_RING] = k1_event(p, L, p - c);
+        head.head += ncopy;
+        if (head.head - head.published >= K1_PUBLISH) k1_publish(ring, head);
         const unsigned last = 31 - clz(CS);
         const uint32_t e_last = last + shfl(L, last);
         if (e_last >= 32) {
@@ -280,22 +321,80 @@ SB_DEVICE bool k1_window(const uint8_t* win, uint32_t n, uint16_t* table, unsign
     return true;
 }
 
-// Parser warp: block already in shared memory, n >= 17.
-SB_DEVICE void k1_parse_block(const uint8_t* win, uint32_t n, uint16_t* table, const K1Ring& ring, uint32_t& head) {
+SB_DEVICE bool k1_window(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
+                         K1State& st, const K1Ring& ring, K1Prod& head) {
+    const K1Pre pre = k1_eval(win, table, shift, st.s & ~31u);
+    return k1_finish(win, n, table, shift, s_limit, st, ring, head, pre);
+}
+
+// Parser warps: block visible through `win`, n >= 17. NP warps take turns over the
+// 32-position windows (window index = position / 32). While it waits for its turn a
+// warp probes its next window against the table as it is NOW (a few inserts stale);
+// when the turn arrives it re-reads the table slots and only re-probes if a slot it
+// depends on changed, so everything except walk+commit is off the critical path.
+//   ctrl[2] = turn (index of the window that may be committed next, DONE when finished)
+//   ctrl[3..5] = parse state (s, skip, rematch)   ctrl[6..7] = ring producer (head, published)
+static const uint32_t K1_DONE = 0xFFFFFFFFu;
+
+template <int NP>
+SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* table, const K1Ring& ring,
+                                  uint32_t* ctrl, unsigned k) {
+    const unsigned lane = lane_id();
     unsigned shift = 24;
     uint32_t tsize = 256;
     while (tsize < 16384 && tsize < n) { shift--; tsize *= 2; }   // src/compress.rs:491-497
     const uint32_t s_limit = n - 15;
-    K1State st;
-    st.s = 1; st.skip = 32; st.rematch = false;
+    K1Prod prod;
+    prod.head = 0; prod.published = 0; prod.tail_seen = 0;
+    uint32_t my = k;
     for (;;) {
-        if (st.rematch) { if (st.s >= s_limit) break; }
-        else if (st.s + (st.skip >> 5) > s_limit) break;
-        const uint32_t w = st.s & ~31u;
-        if (w + 32 < s_limit && (st.rematch || st.skip < 64) &&
-            k1_window(win, n, table, shift, s_limit, st, ring, head))
-            continue;
-        if (k1_serial(win, n, table, shift, s_limit, st, w + 32, ring, head)) break;
+        uint32_t t = shfl(ld_volatile(&ctrl[2]), 0);
+        if (t == K1_DONE) return;
+        if (my < t) my = t + ((k + NP - (t % NP)) % NP);          // first window >= turn that is mine
+        const uint32_t w = my * 32;
+        bool have = false;
+        K1Pre pre;
+        pre.h = pre.c = pre.L = pre.E = 0; pre.eq = false;
+        if (NP > 1 && my != t && w + 32 < s_limit) { pre = k1_eval(win, table, shift, w); have = true; }
+        for (;;) {
+            t = shfl(ld_volatile(&ctrl[2]), 0);
+            if (t >= my) break;
+            spin();
+        }
+        if (t == K1_DONE) return;
+        if (t > my) continue;                                      // my window was jumped over
+        threadfence_block();
+        K1State st;
+        st.s = ld_volatile(&ctrl[3]); st.skip = ld_volatile(&ctrl[4]); st.rematch = ld_volatile(&ctrl[5]) != 0;
+        prod.head = ld_volatile(&ctrl[6]); prod.published = ld_volatile(&ctrl[7]);
+        bool finished;
+        if (st.rematch ? st.s >= s_limit : st.s + (st.skip >> 5) > s_limit) finished = true;
+        else {
+            bool ok = false;
+            if (w + 32 < s_limit && (st.rematch || st.skip < 64)) {
+                if (have) {
+                    const uint32_t cn = table[pre.h];
+                    if (any(lane >= st.s - w && cn != pre.c)) have = false;   // a slot I depend on moved: probe again
+                }
+                if (!have) pre = k1_eval(win, table, shift, w);
+                ok = k1_finish(win, n, table, shift, s_limit, st, ring, prod, pre);
+            }
+            finished = ok ? false : k1_serial(win, n, table, shift, s_limit, st, w + 32, ring, prod);
+        }
+        if (finished) {
+            k1_push(ring, prod, k1_event(n, 0, 0));                // end marker -> trailing literal (:417-426)
+            k1_publish(ring, prod);
+        }
+        syncwarp();
+        if (lane == 0) {
+            ctrl[3] = st.s; ctrl[4] = st.skip; ctrl[5] = st.rematch ? 1u : 0u;
+            ctrl[6] = prod.head; ctrl[7] = prod.published;
+        }
+        threadfence_block();
+        syncwarp();
+        if (lane == 0) st_volatile(&ctrl[2], finished ? K1_DONE : (st.s >> 5));
+        if (finished) return;
+        my += NP;
     }
 }
 #undef K1_HASH
@@ -324,6 +423,9 @@ SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, c
         uint32_t pe = shfl_up(pos + len, 1);
         if (lane == 0) pe = prev_end;
         const uint32_t lit = act ? pos - pe : 0;
+#ifdef SB_EMU_CHECK
+        if (act && (pos < pe || pos > 65536)) fprintf(stderr, "BAD EVENT lane=%u m=%u tail=%u head_pub=%u pos=%u len=%u off=%u pe=%u prev_end=%u\n", lane, m, tail, ld_volatile(&ring.ctrl[0]), pos, len, off, pe, prev_end);
+#endif
         uint32_t lhdr = 0;
         if (lit) lhdr = lit <= 60 ? 1 : lit <= 256 ? 2 : 3;                         // src/compress.rs:436-463
         // copy tags (src/compress.rs:339-356)
@@ -374,17 +476,25 @@ SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, c
     }
 }
 
-// Kernel body: CTA = parser warp + emitter warp, one unit (<= 65536 bytes) at a time.
+// Kernel body: CTA = NP parser warps + one emitter warp, one unit (<= 65536 bytes) at a time.
 // flags bit0: write the varint(length) header in front of the block body.
+// GW = false: the block is staged into a shared-memory window (2 CTAs/SM).
+// GW = true : only the hash table and the event ring live in shared memory and the
+//             window is read in place from global memory/L2 (5 CTAs/SM).
+static const uint32_t K1_SMEM_BYTES_GW = K1_TABLE_BYTES + K1_RING * 8 + 64;
+
+template <bool GW, int NP>
 SB_DEVICE void k1_compress_body(const BatchDesc& b, uint32_t flags) {
-    uint8_t* win = smem();
-    uint16_t* table = (uint16_t*)(win + K1_WIN_BYTES);
+    uint8_t* sm = smem();
+    uint8_t* win_s = sm;                                               // unused when GW
+    uint16_t* table = (uint16_t*)(sm + (GW ? 0 : K1_WIN_BYTES));
     K1Ring ring;
-    ring.ev = (uint64_t*)(win + K1_WIN_BYTES + K1_TABLE_BYTES);
-    ring.ctrl = (uint32_t*)(win + K1_WIN_BYTES + K1_TABLE_BYTES + K1_RING * 8);
-    const unsigned lane = lane_id(), wid = warp_id();
-    uint32_t head = 0, tail = 0;      // parser's / emitter's private ring counters (never reset)
-    if (thread_idx() == 0) { ring.ctrl[0] = 0; ring.ctrl[1] = 0; }
+    ring.ev = (uint64_t*)((uint8_t*)table + K1_TABLE_BYTES);
+    ring.ctrl = (uint32_t*)((uint8_t*)table + K1_TABLE_BYTES + K1_RING * 8);
+    uint32_t* ctrl = ring.ctrl;
+    const unsigned lane = lane_id(), wid = warp_id(), nthreads = (NP + 1) * 32;
+    uint32_t tail = 0;                // emitter's private ring counter (never reset)
+    if (thread_idx() == 0) { ctrl[0] = 0; ctrl[1] = 0; ctrl[6] = 0; ctrl[7] = 0; }
     for (uint32_t u = block_idx(); u < b.count; u += grid_dim()) {
         const uint8_t* in = unit_in(b, u);
         const uint32_t n = unit_in_len(b, u);
@@ -399,20 +509,31 @@ SB_DEVICE void k1_compress_body(const BatchDesc& b, uint32_t flags) {
         }
         if (n == 0) { if (thread_idx() == 0) b.out_lens[u] = d; continue; }
         syncthreads();                                                     // previous unit fully drained
-        // stage the block: each warp copies one half (split on a 16-byte boundary), zero the table
         {
-            const uint32_t half = ((n / 2) + 15) & ~15u;
-            if (wid == 0) warp_copy(win, in, half < n ? half : n);
-            else if (half < n) warp_copy(win + half, in + half, n - half);
-            if (thread_idx() < 16) ((uint32_t*)(win + ((n + 3) & ~3u)))[thread_idx()] = 0;   // defined bytes for over-reads
+            if (!GW) {
+                // stage the block: each warp copies one slice (cut on 16-byte boundaries)
+                const uint32_t per = ((n / (NP + 1)) + 15) & ~15u;
+                const uint32_t lo = per * wid < n ? per * wid : n;
+                const uint32_t hi = (wid == NP || lo + per > n) ? n : lo + per;
+                if (hi > lo) warp_copy(win_s + lo, in + lo, hi - lo);
+                if (thread_idx() < 16) ((uint32_t*)(win_s + ((n + 3) & ~3u)))[thread_idx()] = 0;   // defined bytes for over-reads
+            }
             uint32_t tsize = 256;
             while (tsize < 16384 && tsize < n) tsize *= 2;
-            for (uint32_t i = thread_idx(); i < tsize / 2; i += K1_THREADS) ((uint32_t*)table)[i] = 0;   // (:514-516)
+            for (uint32_t i = thread_idx(); i < tsize / 2; i += nthreads) ((uint32_t*)table)[i] = 0;   // (:514-516)
+            if (thread_idx() == 0) { ctrl[2] = n >= 17 ? 0u : K1_DONE; ctrl[3] = 1; ctrl[4] = 32; ctrl[5] = 0; }
         }
         syncthreads();
-        if (wid == 0) {
-            if (n >= 17) k1_parse_block(win, n, table, ring, head);        // (:140-150)
-            k1_push(ring, head, k1_event(n, 0, 0));                        // end marker -> trailing literal (:417-426)
+        const uint8_t* win = GW ? in : win_s;
+        if (wid < (unsigned)NP) {
+            if (n >= 17) k1_parse_pipelined<NP>(win, n, table, ring, ctrl, wid);   // (:140-150)
+            else if (wid == 0) {                                           // tiny block: one literal (:140-146)
+                K1Prod prod;
+                prod.head = ctrl[6]; prod.published = ctrl[7]; prod.tail_seen = 0;
+                k1_push(ring, prod, k1_event(n, 0, 0));
+                k1_publish(ring, prod);
+                if (lane == 0) { ctrl[6] = prod.head; ctrl[7] = prod.published; }
+            }
         } else {
             d = k1_emit_block(win, out, d, ring, tail);
             if (lane == 0) b.out_lens[u] = d;

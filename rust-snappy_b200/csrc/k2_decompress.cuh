@@ -47,8 +47,8 @@ SB_DEVICE uint32_t k2_decode_stream(const uint8_t* in, uint32_t n, uint8_t* dst,
 
     const uint8_t* src = in + hl;
     const uint8_t* in_end = in + n;
-    const uint64_t sn = n - hl, dn = dn64;
-    uint64_t s = 0, d = 0;
+    const uint32_t sn = n - hl, dn = (uint32_t)dn64;        // both < 2^32 (checked above)
+    uint32_t s = 0, d = 0;
 
     while (s < sn) {
         // ---- fetch 40 bytes starting at the 4-byte-aligned address below src+s
@@ -69,7 +69,7 @@ SB_DEVICE uint32_t k2_decode_stream(const uint8_t* in, uint32_t n, uint8_t* dst,
         const unsigned sh = (bi & 3u) * 8;
         const uint32_t tag = funnel_r(lo, hi, sh) & 0xFFu;          // byte at s+lane
         const uint32_t next4 = sh == 24 ? hi : funnel_r(lo, hi, sh + 8);  // 4 bytes after it
-        const uint64_t rem = sn - s;                                 // bytes left from window start
+        const uint32_t rem = sn - s;                                 // bytes left from window start
         const bool valid = lane < rem;
 
         // ---- speculative element decode (tag layout: build.rs:40-67)
@@ -117,37 +117,44 @@ SB_DEVICE uint32_t k2_decode_stream(const uint8_t* in, uint32_t n, uint8_t* dst,
         }
         const uint32_t opos = incl - olen;
         const uint32_t win_out = shfl(incl, 31);
-        const uint64_t de = d + opos;        // output position of my element
-        const uint64_t sa = s + lane + 1;    // stream position just after my tag byte
+        const uint64_t de = (uint64_t)d + opos;        // output position of my element
+        const uint64_t sa = (uint64_t)s + lane + 1;    // stream position just after my tag byte
 
-        // ---- error conditions in the reference's order of checks
-        uint32_t ecode = 0; uint64_t ea = 0, eb = 0, ec = 0;
-        if (is_start) {
-            if (kind == 0) {
-                uint64_t sp = sa;
-                if ((tag >> 2) >= 60) {
-                    if (sa + 4 > sn) { ecode = SB_LITERAL; ea = 4; eb = sn - sa; ec = dn - de; }  // :192-198
-                    sp = sa + (hdr - 1);
+        // ---- errors. Cheap sufficient test first: 40 more input bytes (no truncated tag),
+        // the whole window's output fits, no spilling literal, every copy offset is in range.
+        // Only when that fails are the reference's checks evaluated element by element.
+        const bool sure = (rem >= 40) && (dn - d >= win_out) &&
+                          !any(is_start && (spill || (kind != 0 && (off == 0 || off > d + opos))));
+        if (!sure) {
+            // error conditions in the reference's order of checks
+            uint32_t ecode = 0; uint64_t ea = 0, eb = 0, ec = 0;
+            if (is_start) {
+                if (kind == 0) {
+                    uint64_t sp = sa;
+                    if ((tag >> 2) >= 60) {
+                        if (sa + 4 > sn) { ecode = SB_LITERAL; ea = 4; eb = sn - sa; ec = dn - de; }  // :192-198
+                        sp = sa + (hdr - 1);
+                    }
+                    if (!ecode && (sn - sp < len || dn - de < len)) {                                   // :209-217
+                        ecode = SB_LITERAL; ea = len; eb = sn - sp; ec = dn - de;
+                    }
+                } else {
+                    const unsigned nb = hdr - 1;
+                    if (sa + 4 > sn) {                                                                  // :439-472
+                        if (nb == 1) { if (sa >= sn) { ecode = SB_COPY_READ; ea = 1; eb = sn - sa; } }
+                        else if (nb == 2) { if (sa + 1 >= sn) { ecode = SB_COPY_READ; ea = 2; eb = sn - sa; } }
+                        else { ecode = SB_COPY_READ; ea = 4; eb = sn - sa; }
+                    }
+                    if (!ecode && (off == 0 || de < off)) { ecode = SB_OFFSET; ea = off; eb = de; }     // :245-250
+                    if (!ecode && de + len > dn) { ecode = SB_COPY_WRITE; ea = len; eb = dn - de; }     // :328-333
                 }
-                if (!ecode && (sn - sp < len || dn - de < len)) {                                   // :209-217
-                    ecode = SB_LITERAL; ea = len; eb = sn - sp; ec = dn - de;
-                }
-            } else {
-                const unsigned nb = hdr - 1;
-                if (sa + 4 > sn) {                                                                  // :439-472
-                    if (nb == 1) { if (sa >= sn) { ecode = SB_COPY_READ; ea = 1; eb = sn - sa; } }
-                    else if (nb == 2) { if (sa + 1 >= sn) { ecode = SB_COPY_READ; ea = 2; eb = sn - sa; } }
-                    else { ecode = SB_COPY_READ; ea = 4; eb = sn - sa; }
-                }
-                if (!ecode && (off == 0 || de < off)) { ecode = SB_OFFSET; ea = off; eb = de; }     // :245-250
-                if (!ecode && de + len > dn) { ecode = SB_COPY_WRITE; ea = len; eb = dn - de; }     // :328-333
             }
-        }
-        const uint32_t emask = ballot(ecode != 0);
-        if (emask) {
-            const unsigned first = ffs(emask) - 1;
-            if (lane == first) set_status(st, ecode, ea, eb, ec);
-            return shfl(ecode, first);
+            const uint32_t emask = ballot(ecode != 0);
+            if (emask) {
+                const unsigned first = ffs(emask) - 1;
+                if (lane == first) set_status(st, ecode, ea, eb, ec);
+                return shfl(ecode, first);
+            }
         }
 
         // ---- literal payload bytes that sit inside the window: lane -> output byte
@@ -161,33 +168,38 @@ SB_DEVICE uint32_t k2_decode_stream(const uint8_t* in, uint32_t n, uint8_t* dst,
         syncwarp();
 
         // ---- copies, replayed in stream order; all lanes move bytes
-        uint32_t cm = ballot(is_start && kind != 0);
-        while (cm) {
-            const unsigned j = ffs(cm) - 1;
-            cm &= cm - 1;
-            const uint32_t pk = shfl((opos << 8) | (uint32_t)len, j);
-            const uint32_t coff = shfl(off, j);
-            const uint32_t clen = pk & 0xFFu;
-            uint8_t* out = dst + d + (pk >> 8);
-            const uint8_t* from = out - coff;
-            if (coff >= clen) {
-                for (uint32_t k = lane; k < clen; k += 32) out[k] = from[k];
-            } else {
-                // overlapping copy = periodic pattern of the last `coff` bytes (:306-317)
-                for (uint32_t k = lane; k < clen; k += 32) out[k] = from[k % coff];
+        {
+            uint8_t* const wout = dst + d;                       // window output base
+            const uint32_t cpk = opos | ((uint32_t)len << 12);   // len <= 64 for copies, opos <= 2048
+            uint32_t cm = ballot(is_start && kind != 0);
+            while (cm) {
+                const unsigned j = ffs(cm) - 1;
+                cm &= cm - 1;
+                const uint32_t pk = shfl(cpk, j), coff = shfl(off, j);
+                const uint32_t clen = pk >> 12;
+                uint8_t* out = wout + (pk & 0xFFFu);
+                if (coff >= clen || clen <= 32) {
+                    // lanes below the offset read final bytes; an overlapping short copy is the
+                    // periodic pattern of the last `coff` bytes (:306-317)
+                    if (lane < clen) out[lane] = out[(int)(coff >= clen || lane < coff ? lane : lane % coff) - (int)coff];
+                    if (clen > 32 && lane + 32 < clen) out[lane + 32] = out[(int)lane + 32 - (int)coff];
+                } else {
+                    const uint8_t* from = out - coff;
+                    for (uint32_t k = lane; k < clen; k += 32) out[k] = from[k % coff];
+                }
+                syncwarp();
             }
-            syncwarp();
         }
 
         // ---- window advance (+ the spilling literal, copied cooperatively)
         const uint32_t lpk = shfl((uint32_t)(spill ? 1u : 0u) | (hdr << 1), last);
         if (lpk & 1u) {
             const uint32_t llen = shfl((uint32_t)len, last);   // validated above: fits in 32 bits
-            const uint64_t lsrc = s + last + (lpk >> 1);
+            const uint32_t lsrc = s + last + (lpk >> 1);
             warp_copy(dst + d + win_out, src + lsrc, llen);
             syncwarp();
             s = lsrc + llen;
-            d += (uint64_t)win_out + llen;
+            d += win_out + llen;
         } else {
             s += shfl(E, 0);
             d += win_out;

@@ -20,7 +20,14 @@
 namespace {
 
 // ------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(64) k1_compress_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body(b, flags); }
+// K1 variants: window in shared memory (S) or read in place from global/L2 (G) x parser warps per block
+__global__ void __launch_bounds__(64) k1_s1_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<false, 1>(b, flags); }
+__global__ void __launch_bounds__(96) k1_s2_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<false, 2>(b, flags); }
+__global__ void __launch_bounds__(128) k1_s3_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<false, 3>(b, flags); }
+__global__ void __launch_bounds__(160) k1_s4_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<false, 4>(b, flags); }
+__global__ void __launch_bounds__(64) k1_g1_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<true, 1>(b, flags); }
+__global__ void __launch_bounds__(96) k1_g2_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<true, 2>(b, flags); }
+__global__ void __launch_bounds__(128) k1_g3_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<true, 3>(b, flags); }
 __global__ void __launch_bounds__(128) k2_decompress_kernel(sb_batch b) { sbk::k2_decompress_body(b); }
 __global__ void __launch_bounds__(256) k3_crc_kernel(sb_batch b) { sbk::k3_crc_body(b); }
 __global__ void __launch_bounds__(256) k4_sizes_kernel(sbk::FramePlan p) { sbk::k4_sizes_body(p); }
@@ -30,6 +37,7 @@ __global__ void __launch_bounds__(256) k5_copy_units_kernel(sb_batch b) { sbk::k
 __global__ void __launch_bounds__(256) k6_generate_kernel(sbk::GenPlan g) { sbk::k6_generate_body(g); }
 
 std::atomic<uint64_t> g_launches{0};
+const int K1_DEFAULT_NP = 2;
 
 int fail(sb_error* e, uint32_t code, uint64_t a = 0, uint64_t b = 0, uint64_t c = 0) {
     if (e) { e->code = code; e->_pad = 0; e->a = a; e->b = b; e->c = c; }
@@ -83,7 +91,13 @@ int get_ctx(Ctx** out, sb_error* err) {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, dev));
         c.dev = dev; c.sms = prop.multiProcessorCount;
-        CK(cudaFuncSetAttribute(k1_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k1_s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k1_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k1_s3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k1_s4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k1_g1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
+        CK(cudaFuncSetAttribute(k1_g2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
+        CK(cudaFuncSetAttribute(k1_g3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
         CK(cudaStreamCreateWithFlags(&c.s_compute, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking));
@@ -104,9 +118,23 @@ int need_pinned(Ctx& c, size_t n, sb_error* err) {
 // ------------------------------------------------------------ launch helpers
 int launch_k1(Ctx& c, const sb_batch& b, uint32_t flags, cudaStream_t st, sb_error* err) {
     if (b.count == 0) return 0;
-    unsigned grid = (unsigned)(2 * c.sms);
+    // K1 variant: SNAPB200_K1_GW=1 reads the window in place from global/L2 (5 CTAs/SM instead of 2),
+    // SNAPB200_K1_NP = parser warps per block (pipelined over windows).
+    static const int gw = getenv("SNAPB200_K1_GW") ? atoi(getenv("SNAPB200_K1_GW")) : 0;
+    static const int np = getenv("SNAPB200_K1_NP") ? atoi(getenv("SNAPB200_K1_NP")) : K1_DEFAULT_NP;
+    unsigned grid = (unsigned)((gw ? 5 : 2) * c.sms);
     if (grid > b.count) grid = b.count;
-    k1_compress_kernel<<<grid, sbk::K1_THREADS, sbk::K1_SMEM_BYTES, st>>>(b, flags);
+    const size_t sm = gw ? sbk::K1_SMEM_BYTES_GW : sbk::K1_SMEM_BYTES;
+    if (gw) {
+        if (np <= 1) k1_g1_kernel<<<grid, 64, sm, st>>>(b, flags);
+        else if (np == 2) k1_g2_kernel<<<grid, 96, sm, st>>>(b, flags);
+        else k1_g3_kernel<<<grid, 128, sm, st>>>(b, flags);
+    } else {
+        if (np <= 1) k1_s1_kernel<<<grid, 64, sm, st>>>(b, flags);
+        else if (np == 2) k1_s2_kernel<<<grid, 96, sm, st>>>(b, flags);
+        else if (np == 3) k1_s3_kernel<<<grid, 128, sm, st>>>(b, flags);
+        else k1_s4_kernel<<<grid, 160, sm, st>>>(b, flags);
+    }
     g_launches++;
     CK(cudaGetLastError());
     return 0;

@@ -6,14 +6,21 @@
 #include "../../rust-snappy_b200/csrc/k2_decompress.cuh"
 
 struct K1Args { sb_batch b; uint32_t flags; };
-static void k1_entry(void* a) { K1Args* x = (K1Args*)a; sbk::k1_compress_body(x->b, x->flags); }
+static void k1_entry(void* a) {
+    K1Args* x = (K1Args*)a;
+    const bool gw = x->flags & 0x100u;
+    const unsigned np = (x->flags >> 12) & 7u, f = x->flags & 0xFFu;
+    if (gw) { if (np <= 1) sbk::k1_compress_body<true, 1>(x->b, f); else if (np == 2) sbk::k1_compress_body<true, 2>(x->b, f); else sbk::k1_compress_body<true, 3>(x->b, f); }
+    else { if (np <= 1) sbk::k1_compress_body<false, 1>(x->b, f); else if (np == 2) sbk::k1_compress_body<false, 2>(x->b, f); else sbk::k1_compress_body<false, 3>(x->b, f); }
+}
 static void k2_entry(void* a) { sbk::k2_decompress_body(*(sb_batch*)a); }
 
 extern "C" {
 
 int emu_compress_batch(const sb_batch* b, uint32_t flags, unsigned grid) {
     K1Args a{*b, flags};
-    sbemu::launch(grid, sbk::K1_THREADS, sbk::K1_SMEM_BYTES, k1_entry, &a);
+    const unsigned np = (flags >> 12) & 7u;
+    sbemu::launch(grid, ((np < 1 ? 1 : np > 3 ? 3 : np) + 1) * 32, sbk::K1_SMEM_BYTES, k1_entry, &a);
     return 0;
 }
 
