@@ -39,12 +39,18 @@ static const uint32_t K1_SMEM_BYTES = K1_WIN_BYTES + K1_TABLE_BYTES + K1_RING * 
 
 // 4 bytes at win+p through two aligned word loads. `win` may be a shared-memory window
 // (4-byte aligned) or the unit's input in global memory (any alignment): the loads are
-// aligned on the absolute address. Callers never ask for bytes past the end of the unit
-// except for the word that contains the last valid byte.
+// aligned on the absolute address.
 SB_DEVICE uint32_t k1_rd32(const uint8_t* win, uint32_t p) {
     const uintptr_t a = (uintptr_t)(win + p);
     const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
     return funnel_r(w[0], w[1], (unsigned)(a & 3u) * 8);
+}
+// same, but never touches a byte at or beyond win+n (zero fill): for positions near the end
+SB_DEVICE uint32_t k1_rd32_end(const uint8_t* win, uint32_t p, uint32_t n) {
+    if (p + 8 <= n) return k1_rd32(win, p);
+    uint32_t v = 0;
+    for (uint32_t k = 0; k < 4; k++) if (p + k < n) v |= (uint32_t)win[p + k] << (8 * k);
+    return v;
 }
 
 // ---------------------------------------------------------------- event ring
@@ -98,7 +104,7 @@ SB_DEVICE uint32_t k1_extend(const uint8_t* win, uint32_t n, uint32_t s, uint32_
         uint32_t m = 0;
         if (p < n) {
             const uint32_t avail = n - p;
-            const uint32_t x = k1_rd32(win, p) ^ k1_rd32(win, c + 4 * lane);
+            const uint32_t x = k1_rd32_end(win, p, n) ^ k1_rd32(win, c + 4 * lane);
             m = x ? (uint32_t)(ffs(x) - 1) >> 3 : 4;
             if (m > avail) m = avail;
         }
@@ -202,8 +208,28 @@ struct K1Pre {
     uint32_t c;      // candidate read from the table
     uint32_t L;      // match length: exact up to 11, 12 = "12 or more"
     uint32_t E;      // ballot: a probe at lane i would hit
+    uint32_t M;      // copy starts reachable from this lane (pointer doubling), valid if !(M & longs)
+    uint32_t longs;  // ballot: hit whose length is only known to be >= 12
     bool eq;
 };
+
+// "next copy start" pointer doubling over the hit lanes of a window
+SB_DEVICE uint32_t k1_double(uint32_t E, bool eq, uint32_t L) {
+    const unsigned lane = lane_id();
+    const uint32_t e = lane + L;
+    uint32_t T = 64;
+    if (eq && e < 32) {
+        if ((E >> e) & 1u) T = e;
+        else { const uint32_t m = e + 1 < 32 ? E >> (e + 1) : 0u; T = m ? e + 1 + (uint32_t)(ffs(m) - 1) : 64; }
+    }
+    uint32_t M = 1u << lane;
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const uint32_t M2 = shfl(M, T & 31u), T2 = shfl(T, T & 31u);
+        if (T < 32) { M |= M2; T = T2; }
+    }
+    return M;
+}
 
 SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w) {
     const uint32_t p = w + lane_id();
@@ -228,6 +254,8 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
         r.L = 8 + (x8 ? (uint32_t)(ffs(x8) - 1) >> 3 : 4);
     }
     r.E = ballot(r.eq);
+    r.longs = ballot(r.eq && r.L == 12);
+    r.M = k1_double(r.E, r.eq, r.L);
     return r;
 }
 
@@ -254,27 +282,19 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         const uint32_t probes = f < 32 ? f - i0 + 1 : 32 - i0;
         if (st.skip + probes > 64) return false;                 // the run leaves stride 1 inside this window
     }
-    // ---- which hits are taken: pointer doubling over "next copy start"
-    uint32_t longmask = ballot(eq && L == 12), CS = 0;
+    // ---- which hits are taken: the probe's pointer doubling, redone only when a taken
+    // copy's length is not exact yet (>= 12): that copy is extended cooperatively first
+    uint32_t longmask = pre.longs, M = pre.M, CS;
     for (;;) {
-        const uint32_t e = lane + L;
-        uint32_t nx = 64;
-        if (eq && e < 32) { nx = ((E >> e) & 1u) ? e : nextbit(e + 1); if (nx >= 32) nx = 64; }
-        uint32_t M = 1u << lane, T = nx;
-        for (int r = 0; r < 5; r++) {
-            const uint32_t M2 = shfl(M, T & 31u), T2 = shfl(T, T & 31u);
-            if (T < 32) { M |= M2; T = T2; }
-            if (r >= 1 && !any(T < 32)) break;            // every chain has left the window
-        }
         CS = f < 32 ? shfl(M, f) : 0;
         const uint32_t unk = CS & longmask;
         if (!unk) break;
-        // the first taken copy whose length is not exact yet: extend it cooperatively
         const unsigned j = ffs(unk) - 1;
         const uint32_t pj = w + j, cj = shfl(c, j);
         const uint32_t end = k1_extend(win, n, pj + 12, cj + 12);
         if (lane == j) L = end - pj;
         longmask &= ~(1u << j);
+        M = k1_double(E, eq, L);
     }
     // ---- inserted positions = entry..31 minus copy interiors [q+1, e-2]
     const bool taken = (CS >> lane) & 1u;
@@ -328,11 +348,13 @@ SB_DEVICE bool k1_window(const uint8_t* win, uint32_t n, uint16_t* table, unsign
 }
 
 // Parser warps: block visible through `win`, n >= 17. NP warps take turns over the
-// 32-position windows (window index = position / 32). While it waits for its turn a
+// 32-position windows (window index = position / 32). While it waits for the token a
 // warp probes its next window against the table as it is NOW (a few inserts stale);
-// when the turn arrives it re-reads the table slots and only re-probes if a slot it
-// depends on changed, so everything except walk+commit is off the critical path.
-//   ctrl[2] = turn (index of the window that may be committed next, DONE when finished)
+// when the token arrives it re-reads the table slots and only re-probes if a slot it
+// depends on moved, so everything except walk+commit is off the critical path.
+// The token travels round-robin over named barriers (bar.arrive -> bar.sync): hardware
+// wake-up, and the barrier orders the shared-memory state/table writes.
+//   ctrl[2] = turn (index of the window to commit next, K1_DONE when the block is finished)
 //   ctrl[3..5] = parse state (s, skip, rematch)   ctrl[6..7] = ring producer (head, published)
 static const uint32_t K1_DONE = 0xFFFFFFFFu;
 
@@ -346,24 +368,24 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
     const uint32_t s_limit = n - 15;
     K1Prod prod;
     prod.head = 0; prod.published = 0; prod.tail_seen = 0;
+    const unsigned bar_mine = 1 + k, bar_next = 1 + (k + 1) % NP;
     uint32_t my = k;
+    bool first = (k == 0);                                         // warp 0 starts with the token
     for (;;) {
-        uint32_t t = shfl(ld_volatile(&ctrl[2]), 0);
-        if (t == K1_DONE) return;
-        if (my < t) my = t + ((k + NP - (t % NP)) % NP);          // first window >= turn that is mine
-        const uint32_t w = my * 32;
+        // probe ahead (stale table) while the token is elsewhere
         bool have = false;
         K1Pre pre;
-        pre.h = pre.c = pre.L = pre.E = 0; pre.eq = false;
-        if (NP > 1 && my != t && w + 32 < s_limit) { pre = k1_eval(win, table, shift, w); have = true; }
-        for (;;) {
-            t = shfl(ld_volatile(&ctrl[2]), 0);
-            if (t >= my) break;
-            spin();
+        pre.h = pre.c = pre.L = pre.E = pre.M = pre.longs = 0; pre.eq = false;
+        uint32_t w = my * 32;
+        if (NP > 1 && !first && w + 32 < s_limit) { pre = k1_eval(win, table, shift, w); have = true; }
+        if (NP > 1 && !first) bar_sync(bar_mine, 64);              // token arrives
+        first = false;
+        const uint32_t t = ld_volatile(&ctrl[2]);
+        if (t == K1_DONE) { if (NP > 1) bar_arrive(bar_next, 64); return; }
+        if (t != my) {
+            if (t % NP != k) { if (NP > 1) bar_arrive(bar_next, 64); continue; }   // not mine: forward the token
+            my = t; w = my * 32; have = false;                     // jumped ahead to a window of mine
         }
-        if (t == K1_DONE) return;
-        if (t > my) continue;                                      // my window was jumped over
-        threadfence_block();
         K1State st;
         st.s = ld_volatile(&ctrl[3]); st.skip = ld_volatile(&ctrl[4]); st.rematch = ld_volatile(&ctrl[5]) != 0;
         prod.head = ld_volatile(&ctrl[6]); prod.published = ld_volatile(&ctrl[7]);
@@ -389,11 +411,13 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
         if (lane == 0) {
             ctrl[3] = st.s; ctrl[4] = st.skip; ctrl[5] = st.rematch ? 1u : 0u;
             ctrl[6] = prod.head; ctrl[7] = prod.published;
+            ctrl[2] = finished ? K1_DONE : (st.s >> 5);
         }
-        threadfence_block();
-        syncwarp();
-        if (lane == 0) st_volatile(&ctrl[2], finished ? K1_DONE : (st.s >> 5));
-        if (finished) return;
+        syncwarp();                                                // state visible to every lane / the next warp
+        if (NP > 1) {
+            bar_arrive(bar_next, 64);                              // pass the token on
+            if (finished) { bar_sync(bar_mine, 64); return; }      // absorb the token when it comes back round
+        } else if (finished) return;
         my += NP;
     }
 }

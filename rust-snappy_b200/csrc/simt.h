@@ -44,6 +44,10 @@ SB_DEVICE void syncthreads() { __syncthreads(); }
 SB_DEVICE void bar_sync(unsigned id, unsigned nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// non-blocking arrival on a named barrier (producer side of a bar.sync/bar.arrive pair)
+SB_DEVICE void bar_arrive(unsigned id, unsigned nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 SB_DEVICE int popc(uint32_t v) { return __popc(v); }
 SB_DEVICE int ffs(uint32_t v) { return __ffs(v); }          // 1-based, 0 if none

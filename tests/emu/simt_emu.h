@@ -135,6 +135,14 @@ SB_DEVICE void bar_sync(unsigned id, unsigned nthreads) {
     f->named_k[id]++;
 }
 
+SB_DEVICE void bar_arrive(unsigned id, unsigned nthreads) {
+    sbemu::Fiber* f = sbemu::g_cur;
+    sbemu::Block* b = f->blk;
+    unsigned g = f->named_k[id] & 1u;
+    if (++b->named_count[id][g] == (int)nthreads) b->named_count[id][g ^ 1u] = 0;
+    f->named_k[id]++;
+}
+
 SB_DEVICE int popc(uint32_t v) { return __builtin_popcount(v); }
 SB_DEVICE int ffs(uint32_t v) { return __builtin_ffs((int)v); }
 SB_DEVICE int clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
