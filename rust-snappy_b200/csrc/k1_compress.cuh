@@ -34,7 +34,8 @@ namespace sbk {
 
 static const uint32_t K1_WIN_BYTES = 65536 + 64;             // window + slack for over-reads
 static const uint32_t K1_TABLE_BYTES = 32768;                // 16K-entry u16 table
-static const uint32_t K1_RING = 1024;                        // copy events in flight
+static const uint32_t K1_RING = 1024;                        // copy events in flight (shared-memory window variant)
+static const uint32_t K1_RING_GW = 256;                      // ... global-window variant (6 CTAs/SM)
 static const uint32_t K1_SMEM_BYTES = K1_WIN_BYTES + K1_TABLE_BYTES + K1_RING * 8 + 64;
 
 // 4 bytes at win+p through two aligned word loads. `win` may be a shared-memory window
@@ -55,8 +56,9 @@ SB_DEVICE uint32_t k1_rd32_end(const uint8_t* win, uint32_t p, uint32_t n) {
 
 // ---------------------------------------------------------------- event ring
 struct K1Ring {
-    uint64_t* ev;        // K1_RING entries
+    uint64_t* ev;        // `size` entries (power of two)
     uint32_t* ctrl;      // [0]=head (produced), [1]=tail (consumed)
+    uint32_t size;
 };
 SB_DEVICE uint64_t k1_event(uint32_t pos, uint32_t len, uint32_t off) {
     return (uint64_t)pos | ((uint64_t)len << 17) | ((uint64_t)off << 34);
@@ -80,17 +82,17 @@ SB_DEVICE void k1_publish(const K1Ring& r, K1Prod& pr) {
     pr.published = pr.head;
 }
 SB_DEVICE void k1_wait_space(const K1Ring& r, K1Prod& pr, uint32_t need) {
-    if (pr.head + need - pr.tail_seen <= K1_RING) return;
+    if (pr.head + need - pr.tail_seen <= r.size) return;
     k1_publish(r, pr);                                   // the emitter must see everything before we wait on it
     for (;;) {
         pr.tail_seen = shfl(ld_volatile(&r.ctrl[1]), 0);   // one reader: the decision must be warp-uniform
-        if (pr.head + need - pr.tail_seen <= K1_RING) return;
+        if (pr.head + need - pr.tail_seen <= r.size) return;
         spin();
     }
 }
 SB_DEVICE void k1_push(const K1Ring& r, K1Prod& pr, uint64_t e) {
     k1_wait_space(r, pr, 1);
-    if (lane_id() == 0) r.ev[pr.head % K1_RING] = e;
+    if (lane_id() == 0) r.ev[pr.head & (r.size - 1)] = e;
     pr.head++;
     if (pr.head - pr.published >= K1_PUBLISH) k1_publish(r, pr);
 }
@@ -212,6 +214,16 @@ struct K1Pre {
     uint32_t longs;  // ballot: hit whose length is only known to be >= 12
     bool eq;
 };
+// the four sequential words a lane needs for a window, fetched one window ahead when the
+// window lives in global memory (hides one L2 round trip per window)
+struct K1Seq { uint32_t a0, a1, a2, a3, w; };
+SB_DEVICE K1Seq k1_fetch_seq(const uint8_t* win, uint32_t w) {
+    const uintptr_t aa = (uintptr_t)(win + w + lane_id());
+    const uint32_t* aw = (const uint32_t*)(aa & ~(uintptr_t)3);
+    K1Seq q;
+    q.a0 = aw[0]; q.a1 = aw[1]; q.a2 = aw[2]; q.a3 = aw[3]; q.w = w;
+    return q;
+}
 
 // "next copy start" pointer doubling over the hit lanes of a window
 SB_DEVICE uint32_t k1_double(uint32_t E, bool eq, uint32_t L) {
@@ -231,13 +243,14 @@ SB_DEVICE uint32_t k1_double(uint32_t E, bool eq, uint32_t L) {
     return M;
 }
 
-SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w) {
+SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w, const K1Seq* seq = nullptr) {
     const uint32_t p = w + lane_id();
     K1Pre r;
     const uintptr_t aa = (uintptr_t)(win + p);
-    const uint32_t* aw = (const uint32_t*)(aa & ~(uintptr_t)3);
     const unsigned ash = (unsigned)(aa & 3u) * 8;
-    const uint32_t a0 = aw[0], a1 = aw[1], a2 = aw[2], a3 = aw[3];
+    uint32_t a0, a1, a2, a3;
+    if (seq && seq->w == w) { a0 = seq->a0; a1 = seq->a1; a2 = seq->a2; a3 = seq->a3; }
+    else { const K1Seq q = k1_fetch_seq(win, w); a0 = q.a0; a1 = q.a1; a2 = q.a2; a3 = q.a3; }
     const uint32_t cur = funnel_r(a0, a1, ash);
     r.h = K1_HASH(cur);
     r.c = table[r.h];
@@ -323,7 +336,7 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
     const uint32_t ncopy = popc(CS);
     if (ncopy) {
         k1_wait_space(ring, head, ncopy);
-        if (taken) ring.ev[(head.head + popc(CS & ((1u << lane) - 1u))) % K1_RING] = k1_event(p, L, p - c);
+        if (taken) ring.ev[(head.head + popc(CS & ((1u << lane) - 1u))) & (ring.size - 1)] = k1_event(p, L, p - c);
         head.head += ncopy;
         if (head.head - head.published >= K1_PUBLISH) k1_publish(ring, head);
         const unsigned last = 31 - clz(CS);
@@ -369,6 +382,8 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
     K1Prod prod;
     prod.head = 0; prod.published = 0; prod.tail_seen = 0;
     const unsigned bar_mine = 1 + k, bar_next = 1 + (k + 1) % NP;
+    K1Seq seq;
+    seq.a0 = seq.a1 = seq.a2 = seq.a3 = 0; seq.w = 0xFFFFFFFFu;
     uint32_t my = k;
     bool first = (k == 0);                                         // warp 0 starts with the token
     for (;;) {
@@ -398,7 +413,12 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
                     const uint32_t cn = table[pre.h];
                     if (any(lane >= st.s - w && cn != pre.c)) have = false;   // a slot I depend on moved: probe again
                 }
-                if (!have) pre = k1_eval(win, table, shift, w);
+                if (!have) {
+                    K1Seq nxt = seq;
+                    if (NP == 1 && w + 96 < n) nxt = k1_fetch_seq(win, w + 32);   // issue next window's loads now
+                    pre = k1_eval(win, table, shift, w, &seq);
+                    seq = nxt;
+                }
                 ok = k1_finish(win, n, table, shift, s_limit, st, ring, prod, pre);
             }
             finished = ok ? false : k1_serial(win, n, table, shift, s_limit, st, w + 32, ring, prod);
@@ -439,7 +459,7 @@ SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, c
         const uint32_t m = avail < 32 ? avail : 32;
         threadfence_block();
         uint64_t ev = 0;
-        if (lane < m) ev = ring.ev[(tail + lane) % K1_RING];
+        if (lane < m) ev = ring.ev[(tail + lane) & (ring.size - 1)];
         const uint32_t pos = (uint32_t)(ev & 0x1FFFFu), len = (uint32_t)((ev >> 17) & 0x1FFFFu), off = (uint32_t)(ev >> 34);
         const bool act = lane < m;
         const bool is_end = act && len == 0;
@@ -505,7 +525,7 @@ SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, c
 // GW = false: the block is staged into a shared-memory window (2 CTAs/SM).
 // GW = true : only the hash table and the event ring live in shared memory and the
 //             window is read in place from global memory/L2 (5 CTAs/SM).
-static const uint32_t K1_SMEM_BYTES_GW = K1_TABLE_BYTES + K1_RING * 8 + 64;
+static const uint32_t K1_SMEM_BYTES_GW = K1_TABLE_BYTES + K1_RING_GW * 8 + 64;
 
 template <bool GW, int NP>
 SB_DEVICE void k1_compress_body(const BatchDesc& b, uint32_t flags) {
@@ -513,8 +533,9 @@ SB_DEVICE void k1_compress_body(const BatchDesc& b, uint32_t flags) {
     uint8_t* win_s = sm;                                               // unused when GW
     uint16_t* table = (uint16_t*)(sm + (GW ? 0 : K1_WIN_BYTES));
     K1Ring ring;
+    ring.size = GW ? K1_RING_GW : K1_RING;
     ring.ev = (uint64_t*)((uint8_t*)table + K1_TABLE_BYTES);
-    ring.ctrl = (uint32_t*)((uint8_t*)table + K1_TABLE_BYTES + K1_RING * 8);
+    ring.ctrl = (uint32_t*)((uint8_t*)table + K1_TABLE_BYTES + ring.size * 8);
     uint32_t* ctrl = ring.ctrl;
     const unsigned lane = lane_id(), wid = warp_id(), nthreads = (NP + 1) * 32;
     uint32_t tail = 0;                // emitter's private ring counter (never reset)

@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(256) k5_copy_units_kernel(sb_batch b) { sbk::k
 __global__ void __launch_bounds__(256) k6_generate_kernel(sbk::GenPlan g) { sbk::k6_generate_body(g); }
 
 std::atomic<uint64_t> g_launches{0};
-const int K1_DEFAULT_NP = 2;
+const int K1_DEFAULT_NP = 1;
+const int K1_DEFAULT_GW = 1;
 
 int fail(sb_error* e, uint32_t code, uint64_t a = 0, uint64_t b = 0, uint64_t c = 0) {
     if (e) { e->code = code; e->_pad = 0; e->a = a; e->b = b; e->c = c; }
@@ -118,11 +119,11 @@ int need_pinned(Ctx& c, size_t n, sb_error* err) {
 // ------------------------------------------------------------ launch helpers
 int launch_k1(Ctx& c, const sb_batch& b, uint32_t flags, cudaStream_t st, sb_error* err) {
     if (b.count == 0) return 0;
-    // K1 variant: SNAPB200_K1_GW=1 reads the window in place from global/L2 (5 CTAs/SM instead of 2),
+    // K1 variant: SNAPB200_K1_GW=1 (default) reads the window in place from global/L2 (6 CTAs/SM instead of 2),
     // SNAPB200_K1_NP = parser warps per block (pipelined over windows).
-    static const int gw = getenv("SNAPB200_K1_GW") ? atoi(getenv("SNAPB200_K1_GW")) : 0;
+    static const int gw = getenv("SNAPB200_K1_GW") ? atoi(getenv("SNAPB200_K1_GW")) : K1_DEFAULT_GW;
     static const int np = getenv("SNAPB200_K1_NP") ? atoi(getenv("SNAPB200_K1_NP")) : K1_DEFAULT_NP;
-    unsigned grid = (unsigned)((gw ? 5 : 2) * c.sms);
+    unsigned grid = (unsigned)((gw ? 6 : 2) * c.sms);
     if (grid > b.count) grid = b.count;
     const size_t sm = gw ? sbk::K1_SMEM_BYTES_GW : sbk::K1_SMEM_BYTES;
     if (gw) {
