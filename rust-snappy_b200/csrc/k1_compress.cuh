@@ -454,7 +454,7 @@ SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, c
             avail = ld_volatile(&ring.ctrl[0]) - tail;
             avail = shfl(avail, 0);
             if (avail) break;
-            spin();
+            spin_long();
         }
         const uint32_t m = avail < 32 ? avail : 32;
         threadfence_block();

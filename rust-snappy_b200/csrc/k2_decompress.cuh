@@ -167,17 +167,42 @@ SB_DEVICE uint32_t k2_decode_stream(const uint8_t* in, uint32_t n, uint8_t* dst,
         }
         syncwarp();
 
-        // ---- copies, replayed in stream order; all lanes move bytes
+        // ---- copies. A copy whose source lies entirely before this window's output
+        // (offset >= opos + len) depends on nothing written in this window: those are
+        // issued four at a time, loads first, so their L2 round trips overlap. The rest
+        // (recent/overlapping sources, lengths above 32) are replayed one by one in stream order.
         {
             uint8_t* const wout = dst + d;                       // window output base
             const uint32_t cpk = opos | ((uint32_t)len << 12);   // len <= 64 for copies, opos <= 2048
-            uint32_t cm = ballot(is_start && kind != 0);
+            const bool is_copy = is_start && kind != 0;
+            const bool indep = is_copy && (uint32_t)len <= 32 && off >= opos + (uint32_t)len;
+            uint32_t ic = ballot(indep);
+            while (ic) {
+                uint32_t pk[4], co[4];
+                uint8_t v[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const unsigned j = ic ? ffs(ic) - 1 : 0;
+                    const bool on = ic != 0;
+                    ic &= ic - 1;
+                    pk[q] = shfl(cpk, j); co[q] = shfl(off, j);
+                    if (!on) pk[q] = 0;                          // length 0: nothing to do
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    v[q] = lane < (pk[q] >> 12) ? (wout + (pk[q] & 0xFFFu))[(int)lane - (int)co[q]] : (uint8_t)0;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (lane < (pk[q] >> 12)) (wout + (pk[q] & 0xFFFu))[lane] = v[q];
+            }
+            syncwarp();
+            uint32_t cm = ballot(is_copy && !indep);
             while (cm) {
                 const unsigned j = ffs(cm) - 1;
                 cm &= cm - 1;
-                const uint32_t pk = shfl(cpk, j), coff = shfl(off, j);
-                const uint32_t clen = pk >> 12;
-                uint8_t* out = wout + (pk & 0xFFFu);
+                const uint32_t pk1 = shfl(cpk, j), coff = shfl(off, j);
+                const uint32_t clen = pk1 >> 12;
+                uint8_t* out = wout + (pk1 & 0xFFFu);
                 if (coff >= clen || clen <= 32) {
                     // lanes below the offset read final bytes; an overlapping short copy is the
                     // periodic pattern of the last `coff` bytes (:306-317)

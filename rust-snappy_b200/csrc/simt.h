@@ -66,6 +66,7 @@ SB_DEVICE uint32_t reduce_add(uint32_t v) { return __reduce_add_sync(SB_FULL, v)
 SB_DEVICE uint32_t reduce_max(uint32_t v) { return __reduce_max_sync(SB_FULL, v); }
 // polite spin-wait hint inside producer/consumer polling loops
 SB_DEVICE void spin() { __nanosleep(32); }
+SB_DEVICE void spin_long() { __nanosleep(1500); }   // consumer side: latency does not matter, issue slots do
 SB_DEVICE uint32_t ld_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 SB_DEVICE void st_volatile(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
 

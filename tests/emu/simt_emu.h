@@ -187,6 +187,7 @@ SB_DEVICE uint32_t reduce_max(uint32_t v) {
     return r;
 }
 SB_DEVICE void spin() { sbemu::yield(); }
+SB_DEVICE void spin_long() { sbemu::yield(); }
 SB_DEVICE uint32_t ld_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 SB_DEVICE void st_volatile(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
 
