@@ -570,9 +570,17 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     std::vector<Wave> waves = plan_waves(in_lens, count, out_caps);
-    for (size_t wi = 0; wi < waves.size(); wi++) {
+    cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
+    for (int k = 0; k < 2; k++) {
+        CK(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_k[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
+    }
+    std::vector<uint64_t> pin[2], pout[2];
+    // H2D of wave wi into buffer set wi&1 (copy stream; overlaps the previous wave's kernel)
+    auto stage_in = [&](size_t wi) -> int {
         const Wave& w = waves[wi];
-        const int b = 0;
+        const int b = (int)(wi & 1);
         uint64_t out_total = 0;
         for (size_t k = 0; k < w.count; k++) out_total += ((uint64_t)out_caps[w.first + k] + 15) & ~(uint64_t)15;
         CK(c->in[b].need(w.in_bytes + 64));
@@ -582,28 +590,37 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
         CK(c->status[b].need(w.count * sizeof(sb_error)));
         CK(c->ptrs_in[b].need(w.count * 8 + 8));
         CK(c->ptrs_out[b].need(w.count * 8 + 8));
-        std::vector<uint64_t> pin(w.count), pout(w.count);
+        pin[b].resize(w.count); pout[b].resize(w.count);
         uint64_t at = 0, oat = 0;
         size_t i = 0;
-        while (i < w.count) {
+        while (i < w.count) {                                      // host-contiguous units travel as one copy
             size_t j = i;
             uint64_t run = 0;
             const uint64_t h0 = in_offs[w.first + i];
             while (j < w.count && in_offs[w.first + j] == h0 + run) {
-                pin[j] = (uint64_t)(uintptr_t)(c->in[b].as<uint8_t>() + at + run); run += in_lens[w.first + j]; j++;
+                pin[b][j] = (uint64_t)(uintptr_t)(c->in[b].as<uint8_t>() + at + run); run += in_lens[w.first + j]; j++;
             }
-            if (run) CK(cudaMemcpyAsync(c->in[b].as<uint8_t>() + at, in_base + h0, run, cudaMemcpyHostToDevice, c->s_compute));
+            if (run) CK(cudaMemcpyAsync(c->in[b].as<uint8_t>() + at, in_base + h0, run, cudaMemcpyHostToDevice, c->s_h2d));
             at += (run + 15) & ~(uint64_t)15;
             i = j;
         }
         for (size_t k = 0; k < w.count; k++) {
-            pout[k] = (uint64_t)(uintptr_t)(c->compact[b].as<uint8_t>() + oat);
+            pout[b][k] = (uint64_t)(uintptr_t)(c->compact[b].as<uint8_t>() + oat);
             oat += ((uint64_t)out_caps[w.first + k] + 15) & ~(uint64_t)15;
         }
-        CK(cudaMemcpyAsync(c->ptrs_in[b].p, pin.data(), w.count * 8, cudaMemcpyHostToDevice, c->s_compute));
-        CK(cudaMemcpyAsync(c->ptrs_out[b].p, pout.data(), w.count * 8, cudaMemcpyHostToDevice, c->s_compute));
-        CK(cudaMemcpyAsync(c->caps[b].p, in_lens + w.first, w.count * 4, cudaMemcpyHostToDevice, c->s_compute));
-        CK(cudaMemcpyAsync(c->caps[b].as<uint32_t>() + w.count, out_caps + w.first, w.count * 4, cudaMemcpyHostToDevice, c->s_compute));
+        CK(cudaMemcpyAsync(c->ptrs_in[b].p, pin[b].data(), w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
+        CK(cudaMemcpyAsync(c->ptrs_out[b].p, pout[b].data(), w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
+        CK(cudaMemcpyAsync(c->caps[b].p, in_lens + w.first, w.count * 4, cudaMemcpyHostToDevice, c->s_h2d));
+        CK(cudaMemcpyAsync(c->caps[b].as<uint32_t>() + w.count, out_caps + w.first, w.count * 4, cudaMemcpyHostToDevice, c->s_h2d));
+        CK(cudaStreamSynchronize(c->s_h2d));
+        CK(cudaEventRecord(ev_in[b], c->s_h2d));
+        return 0;
+    };
+    if (!waves.empty()) { rc = stage_in(0); if (rc) return rc; }
+    for (size_t wi = 0; wi < waves.size(); wi++) {
+        const Wave& w = waves[wi];
+        const int b = (int)(wi & 1);
+        CK(cudaStreamWaitEvent(c->s_compute, ev_in[b], 0));
         sb_batch bt;
         memset(&bt, 0, sizeof bt);
         bt.in_ptrs = (const uint8_t* const*)c->ptrs_in[b].p; bt.in_lens = c->caps[b].as<uint32_t>();
@@ -613,16 +630,19 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
         if (rc) return rc;
         CK(cudaMemcpyAsync(out_lens + w.first, c->lens[b].p, w.count * 4, cudaMemcpyDeviceToHost, c->s_compute));
         CK(cudaMemcpyAsync(statuses + w.first, c->status[b].p, w.count * sizeof(sb_error), cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaStreamSynchronize(c->s_compute));
-        // drain; contiguous destinations whose caps are exactly filled go out as one copy
+        CK(cudaEventRecord(ev_k[b], c->s_compute));
+        if (wi >= 1) CK(cudaEventSynchronize(ev_out[b ^ 1]));       // wave wi-1 drained: its buffers may be restaged
+        if (wi + 1 < waves.size()) { rc = stage_in(wi + 1); if (rc) return rc; }   // overlaps the kernel above
+        CK(cudaEventSynchronize(ev_k[b]));
+        // drain on the third stream; contiguous destinations whose caps are exactly filled go out as one copy
+        const uint64_t cbase = (uint64_t)(uintptr_t)c->compact[b].p;
         size_t k = 0;
         while (k < w.count) {
             size_t j = k;
             uint64_t run = 0;
             const uint64_t h0 = out_offs[w.first + k];
-            const uint64_t d0 = pout[k] - (uint64_t)(uintptr_t)c->compact[b].p;
-            while (j < w.count && out_offs[w.first + j] == h0 + run &&
-                   pout[j] - (uint64_t)(uintptr_t)c->compact[b].p == d0 + run) {
+            const uint64_t d0 = pout[b][k] - cbase;
+            while (j < w.count && out_offs[w.first + j] == h0 + run && pout[b][j] - cbase == d0 + run) {
                 run += out_lens[w.first + j];
                 const bool full = out_lens[w.first + j] == out_caps[w.first + j] && (out_caps[w.first + j] & 15u) == 0;
                 j++;
@@ -631,8 +651,11 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
             if (run) CK(cudaMemcpyAsync(out_base + h0, c->compact[b].as<uint8_t>() + d0, run, cudaMemcpyDeviceToHost, c->s_d2h));
             k = j;
         }
-        CK(cudaStreamSynchronize(c->s_d2h));
+        CK(cudaEventRecord(ev_out[b], c->s_d2h));
     }
+    CK(cudaStreamSynchronize(c->s_d2h));
+    CK(cudaStreamSynchronize(c->s_compute));
+    for (int k = 0; k < 2; k++) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_k[k]); cudaEventDestroy(ev_out[k]); }
     ok(err);
     return 0;
 }
