@@ -214,31 +214,17 @@ struct K1Pre {
     uint32_t longs;  // ballot: hit whose length is only known to be >= 12
     bool eq;
 };
-// Software pipeline for the global-memory window: the four sequential words of a lane are
-// fetched two windows ahead, and one window ahead the table is read (stale by one window) and
-// the four candidate words are fetched. When the window is finally probed the table is read
-// again: lanes whose slot did not move already hold their candidate words, the others reload.
-struct K1Seq {
-    uint32_t a0, a1, a2, a3, w;      // sequential words of window w
-    uint32_t h, c, b0, b1, b2, b3;   // hash, (stale) candidate and its words, valid if hasb
-    bool hasb;
-};
-SB_DEVICE K1Seq k1_fetch_a(const uint8_t* win, uint32_t w) {
+// the four sequential words a lane needs for a window, fetched one window ahead when the
+// window lives in global memory (hides one L2 round trip per window)
+struct K1Seq { uint32_t a0, a1, a2, a3, w; };
+SB_DEVICE K1Seq k1_fetch_seq(const uint8_t* win, uint32_t w) {
     const uintptr_t aa = (uintptr_t)(win + w + lane_id());
     const uint32_t* aw = (const uint32_t*)(aa & ~(uintptr_t)3);
     K1Seq q;
     q.a0 = aw[0]; q.a1 = aw[1]; q.a2 = aw[2]; q.a3 = aw[3]; q.w = w;
-    q.h = q.c = q.b0 = q.b1 = q.b2 = q.b3 = 0; q.hasb = false;
     return q;
 }
-SB_DEVICE void k1_fetch_b(const uint8_t* win, const uint16_t* table, unsigned shift, K1Seq& q) {
-    const unsigned ash = (unsigned)((uintptr_t)(win + q.w + lane_id()) & 3u) * 8;
-    q.h = K1_HASH(funnel_r(q.a0, q.a1, ash));
-    q.c = table[q.h];
-    const uint32_t* bw = (const uint32_t*)((uintptr_t)(win + q.c) & ~(uintptr_t)3);
-    q.b0 = bw[0]; q.b1 = bw[1]; q.b2 = bw[2]; q.b3 = bw[3];
-    q.hasb = true;
-}
+
 // "next copy start" pointer doubling over the hit lanes of a window
 SB_DEVICE uint32_t k1_double(uint32_t E, bool eq, uint32_t L) {
     const unsigned lane = lane_id();
@@ -262,21 +248,16 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
     K1Pre r;
     const uintptr_t aa = (uintptr_t)(win + p);
     const unsigned ash = (unsigned)(aa & 3u) * 8;
-    const bool pre_a = seq && seq->w == w;
     uint32_t a0, a1, a2, a3;
-    if (pre_a) { a0 = seq->a0; a1 = seq->a1; a2 = seq->a2; a3 = seq->a3; }
-    else { const K1Seq q = k1_fetch_a(win, w); a0 = q.a0; a1 = q.a1; a2 = q.a2; a3 = q.a3; }
+    if (seq && seq->w == w) { a0 = seq->a0; a1 = seq->a1; a2 = seq->a2; a3 = seq->a3; }
+    else { const K1Seq q = k1_fetch_seq(win, w); a0 = q.a0; a1 = q.a1; a2 = q.a2; a3 = q.a3; }
     const uint32_t cur = funnel_r(a0, a1, ash);
     r.h = K1_HASH(cur);
     r.c = table[r.h];
     const uintptr_t ba = (uintptr_t)(win + r.c);
+    const uint32_t* bw = (const uint32_t*)(ba & ~(uintptr_t)3);
     const unsigned bsh = (unsigned)(ba & 3u) * 8;
-    uint32_t b0, b1, b2, b3;
-    if (pre_a && seq->hasb && seq->c == r.c) { b0 = seq->b0; b1 = seq->b1; b2 = seq->b2; b3 = seq->b3; }
-    else {
-        const uint32_t* bw = (const uint32_t*)(ba & ~(uintptr_t)3);
-        b0 = bw[0]; b1 = bw[1]; b2 = bw[2]; b3 = bw[3];
-    }
+    const uint32_t b0 = bw[0], b1 = bw[1], b2 = bw[2], b3 = bw[3];
     r.eq = cur == funnel_r(b0, b1, bsh);
     r.L = 4;
     const uint32_t x4 = funnel_r(a1, a2, ash) ^ funnel_r(b1, b2, bsh);
@@ -390,7 +371,7 @@ SB_DEVICE bool k1_window(const uint8_t* win, uint32_t n, uint16_t* table, unsign
 //   ctrl[3..5] = parse state (s, skip, rematch)   ctrl[6..7] = ring producer (head, published)
 static const uint32_t K1_DONE = 0xFFFFFFFFu;
 
-template <int NP, bool GW_PIPE>
+template <int NP>
 SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* table, const K1Ring& ring,
                                   uint32_t* ctrl, unsigned k) {
     const unsigned lane = lane_id();
@@ -401,10 +382,8 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
     K1Prod prod;
     prod.head = 0; prod.published = 0; prod.tail_seen = 0;
     const unsigned bar_mine = 1 + k, bar_next = 1 + (k + 1) % NP;
-    K1Seq seq0, seq1;                                              // this window / next window
-    seq0.a0 = seq0.a1 = seq0.a2 = seq0.a3 = 0; seq0.w = 0xFFFFFFFFu;
-    seq0.h = seq0.c = seq0.b0 = seq0.b1 = seq0.b2 = seq0.b3 = 0; seq0.hasb = false;
-    seq1 = seq0;
+    K1Seq seq;
+    seq.a0 = seq.a1 = seq.a2 = seq.a3 = 0; seq.w = 0xFFFFFFFFu;
     uint32_t my = k;
     bool first = (k == 0);                                         // warp 0 starts with the token
     for (;;) {
@@ -435,19 +414,10 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
                     if (any(lane >= st.s - w && cn != pre.c)) have = false;   // a slot I depend on moved: probe again
                 }
                 if (!have) {
-                    if (NP == 1 && GW_PIPE) {
-                        // next window: sequential words are here by now -> stale table read + candidate loads
-                        if (seq1.w != w + 32 && w + 96 <= n) seq1 = k1_fetch_a(win, w + 32);
-                        if (seq1.w == w + 32 && !seq1.hasb) k1_fetch_b(win, table, shift, seq1);
-                        // window after next: sequential words
-                        K1Seq seq2 = seq0;
-                        seq2.w = 0xFFFFFFFFu; seq2.hasb = false;
-                        if (w + 128 <= n) seq2 = k1_fetch_a(win, w + 64);
-                        pre = k1_eval(win, table, shift, w, &seq0);
-                        seq0 = seq1; seq1 = seq2;
-                    } else {
-                        pre = k1_eval(win, table, shift, w);
-                    }
+                    K1Seq nxt = seq;
+                    if (NP == 1 && w + 96 < n) nxt = k1_fetch_seq(win, w + 32);   // issue next window's loads now
+                    pre = k1_eval(win, table, shift, w, &seq);
+                    seq = nxt;
                 }
                 ok = k1_finish(win, n, table, shift, s_limit, st, ring, prod, pre);
             }
@@ -601,7 +571,7 @@ SB_DEVICE void k1_compress_body(const BatchDesc& b, uint32_t flags) {
         syncthreads();
         const uint8_t* win = GW ? in : win_s;
         if (wid < (unsigned)NP) {
-            if (n >= 17) k1_parse_pipelined<NP, GW>(win, n, table, ring, ctrl, wid);   // (:140-150)
+            if (n >= 17) k1_parse_pipelined<NP>(win, n, table, ring, ctrl, wid);   // (:140-150)
             else if (wid == 0) {                                           // tiny block: one literal (:140-146)
                 K1Prod prod;
                 prod.head = ctrl[6]; prod.published = ctrl[7]; prod.tail_seen = 0;
