@@ -126,6 +126,17 @@ int sb_frame_decode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_
 int sb_frame_encode_device(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap,
                            int include_ident, uint64_t* out_n, void* stream, sb_error* err);
 
+/* ---- libsnappy-compatible C API ------------------------------------------
+ * The four functions the reference's `snappy-cpp` crate binds
+ * (snappy-cpp/src/lib.rs:66-88, snappy-c.h): linking the reference's test/ and
+ * bench/ crates with `--features cpp` against this library runs their
+ * cross-implementation tests on the GPU codec. 0 = SNAPPY_OK, 1 = INVALID_INPUT,
+ * 2 = BUFFER_TOO_SMALL. */
+int snappy_compress(const char* input, size_t input_length, char* compressed, size_t* compressed_length);
+int snappy_uncompress(const char* compressed, size_t compressed_length, char* uncompressed, size_t* uncompressed_length);
+size_t snappy_max_compressed_length(size_t source_length);
+int snappy_uncompressed_length(const char* compressed, size_t compressed_length, size_t* result);
+
 /* ---- misc ---------------------------------------------------------------- */
 /* Number of kernel launches issued by this library since load (bench.py's
  * gpu_launches evidence). */

@@ -33,6 +33,7 @@ SYMBOLS = [
     "sb_compress_batch_device", "sb_decompress_batch_device", "sb_crc32c_masked_batch_device",
     "sb_frame_max_len", "sb_frame_encode", "sb_frame_encode_ex", "sb_frame_decode", "sb_frame_encode_device",
     "sb_launch_count", "sb_generate_blocks_device", "sb_version",
+    "snappy_compress", "snappy_uncompress", "snappy_max_compressed_length", "snappy_uncompressed_length",
 ]
 
 _lib = None
@@ -70,5 +71,10 @@ def lib():
     L.sb_frame_encode_device.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.c_int, u64p, vp, ep]
     L.sb_generate_blocks_device.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.c_uint64,
                                             C.c_uint64, C.c_uint64, vp, ep]
+    L.snappy_max_compressed_length.restype = sz
+    L.snappy_max_compressed_length.argtypes = [sz]
+    L.snappy_compress.argtypes = [vp, sz, vp, szp]
+    L.snappy_uncompress.argtypes = [vp, sz, vp, szp]
+    L.snappy_uncompressed_length.argtypes = [vp, sz, szp]
     _lib = L
     return L

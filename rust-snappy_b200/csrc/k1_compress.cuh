@@ -385,6 +385,8 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
     K1Seq seq;
     seq.a0 = seq.a1 = seq.a2 = seq.a3 = 0; seq.w = 0xFFFFFFFFu;
     uint32_t my = k;
+    K1State lst;                                                   // NP == 1: parse state kept in registers
+    lst.s = 1; lst.skip = 32; lst.rematch = false;
     bool first = (k == 0);                                         // warp 0 starts with the token
     for (;;) {
         // probe ahead (stale table) while the token is elsewhere
@@ -395,15 +397,22 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
         if (NP > 1 && !first && w + 32 < s_limit) { pre = k1_eval(win, table, shift, w); have = true; }
         if (NP > 1 && !first) bar_sync(bar_mine, 64);              // token arrives
         first = false;
-        const uint32_t t = ld_volatile(&ctrl[2]);
-        if (t == K1_DONE) { if (NP > 1) bar_arrive(bar_next, 64); return; }
-        if (t != my) {
-            if (t % NP != k) { if (NP > 1) bar_arrive(bar_next, 64); continue; }   // not mine: forward the token
-            my = t; w = my * 32; have = false;                     // jumped ahead to a window of mine
-        }
         K1State st;
-        st.s = ld_volatile(&ctrl[3]); st.skip = ld_volatile(&ctrl[4]); st.rematch = ld_volatile(&ctrl[5]) != 0;
-        prod.head = ld_volatile(&ctrl[6]); prod.published = ld_volatile(&ctrl[7]);
+        if (NP == 1) {
+            // single parser: state lives in registers, only the producer counters persist across units
+            if (my == 0) { lst.s = 1; lst.skip = 32; lst.rematch = false; prod.head = ld_volatile(&ctrl[6]); prod.published = ld_volatile(&ctrl[7]); }
+            st = lst;
+            my = st.s >> 5; w = my * 32;
+        } else {
+            const uint32_t t = ld_volatile(&ctrl[2]);
+            if (t == K1_DONE) { bar_arrive(bar_next, 64); return; }
+            if (t != my) {
+                if (t % NP != k) { bar_arrive(bar_next, 64); continue; }   // not mine: forward the token
+                my = t; w = my * 32; have = false;                 // jumped ahead to a window of mine
+            }
+            st.s = ld_volatile(&ctrl[3]); st.skip = ld_volatile(&ctrl[4]); st.rematch = ld_volatile(&ctrl[5]) != 0;
+            prod.head = ld_volatile(&ctrl[6]); prod.published = ld_volatile(&ctrl[7]);
+        }
         bool finished;
         if (st.rematch ? st.s >= s_limit : st.s + (st.skip >> 5) > s_limit) finished = true;
         else {
@@ -426,6 +435,16 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
         if (finished) {
             k1_push(ring, prod, k1_event(n, 0, 0));                // end marker -> trailing literal (:417-426)
             k1_publish(ring, prod);
+        }
+        if (NP == 1) {
+            lst = st;
+            if (finished) {
+                syncwarp();
+                if (lane == 0) { ctrl[6] = prod.head; ctrl[7] = prod.published; }
+                return;
+            }
+            my = 1;                                                // any non-zero value: "not the first window"
+            continue;
         }
         syncwarp();
         if (lane == 0) {

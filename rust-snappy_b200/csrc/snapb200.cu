@@ -865,4 +865,32 @@ int sb_frame_decode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_
     return 0;
 }
 
+// ---------------------------------------------------------- libsnappy C API
+int snappy_compress(const char* input, size_t input_length, char* compressed, size_t* compressed_length) {
+    if (!compressed_length) return 1;
+    sb_error e;
+    size_t n = 0;
+    int rc = sb_compress((const uint8_t*)input, input_length, (uint8_t*)compressed, *compressed_length, &n, &e);
+    if (rc == SB_BUFFER_TOO_SMALL) return 2;
+    if (rc) return 1;
+    *compressed_length = n;
+    return 0;
+}
+int snappy_uncompress(const char* compressed, size_t compressed_length, char* uncompressed, size_t* uncompressed_length) {
+    if (!uncompressed_length) return 1;
+    sb_error e;
+    size_t n = 0;
+    int rc = sb_decompress((const uint8_t*)compressed, compressed_length, (uint8_t*)uncompressed, *uncompressed_length, &n, &e);
+    if (rc == SB_BUFFER_TOO_SMALL) return 2;
+    if (rc) return 1;
+    *uncompressed_length = n;
+    return 0;
+}
+size_t snappy_max_compressed_length(size_t source_length) { return 32 + source_length + source_length / 6; }
+int snappy_uncompressed_length(const char* compressed, size_t compressed_length, size_t* result) {
+    sb_error e;
+    if (!result || compressed_length == 0) return 1;
+    return sb_decompress_len((const uint8_t*)compressed, compressed_length, result, &e) ? 1 : 0;
+}
+
 }  // extern "C"

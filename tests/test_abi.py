@@ -19,7 +19,7 @@ def snap():
 
 def test_header_symbols_exported(snap):
     hdr = open(os.path.join(ROOT, "include", "snapb200.h")).read()
-    declared = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b((?:sb|snappy)_[a-z0-9_]+)\s*\(", hdr))
     lib = snap._lib.lib()
     assert declared == set(snap._lib.SYMBOLS)
     for name in declared:

@@ -309,3 +309,25 @@ def test_gpu_sharded_frame_encode(snap, oracle):
     torch.cuda.synchronize()
     assert b"".join(parts) == oracle.frame_encode(data)
     assert snap.frame.decode_all(b"".join(parts)) == data
+
+
+def test_libsnappy_compatible_symbols(snap, oracle):
+    """snappy_compress / snappy_uncompress / ... as bound by the reference's snappy-cpp crate
+    (snappy-cpp/src/lib.rs:13-88): Rust decompresses "cpp", "cpp" decompresses Rust."""
+    import ctypes as C
+    L = snap._lib.lib()
+    data = corpus("geo.protodata")
+    cap = L.snappy_max_compressed_length(len(data))
+    assert cap == snap.raw.max_compress_len(len(data))
+    buf, n = C.create_string_buffer(cap), C.c_size_t(cap)
+    assert L.snappy_compress(data, len(data), buf, C.byref(n)) == 0
+    comp = buf.raw[:n.value]
+    assert comp == oracle.compress(data)
+    m = C.c_size_t(0)
+    assert L.snappy_uncompressed_length(comp, len(comp), C.byref(m)) == 0 and m.value == len(data)
+    out, k = C.create_string_buffer(len(data)), C.c_size_t(len(data))
+    assert L.snappy_uncompress(comp, len(comp), out, C.byref(k)) == 0 and out.raw[:k.value] == data
+    small = C.c_size_t(10)
+    assert L.snappy_compress(data, len(data), buf, C.byref(small)) == 2          # SNAPPY_BUFFER_TOO_SMALL
+    bad, k2 = b"\x05\x00a", C.c_size_t(16)
+    assert L.snappy_uncompress(bad, 3, out, C.byref(k2)) == 1                      # SNAPPY_INVALID_INPUT
