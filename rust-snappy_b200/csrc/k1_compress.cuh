@@ -297,7 +297,7 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
     }
     // ---- which hits are taken: the probe's pointer doubling, redone only when a taken
     // copy's length is not exact yet (>= 12): that copy is extended cooperatively first
-    uint32_t longmask = pre.longs, M = pre.M, CS;
+    uint32_t longmask = pre.longs, M = pre.M, CS;   // CS: lanes whose hit is taken as a copy
     for (;;) {
         CS = f < 32 ? shfl(M, f) : 0;
         const uint32_t unk = CS & longmask;
@@ -326,11 +326,44 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
     if (ins) table[h] = (uint16_t)p;
     syncwarp();
     const bool clash = ins && table[h] != (uint16_t)p;
-    if (any(clash)) {                                            // two inserted lanes share a slot: undo, replay serially
+    uint32_t cut = 32;                                           // window accepted up to (not including) this lane
+    if (any(clash)) {
+        // Two inserted lanes share a slot. A probed lane with a lower inserted lane of the same
+        // hash should have seen that lane as its candidate ("victim"): everything before the
+        // first victim is still exactly what the serial encoder does, so keep that prefix and
+        // restart the window at the victim. Copy-end pre-inserts (e-1) are write-only, never victims.
+        const uint32_t same = match_any(ins ? h : 0xFFFF0000u | lane);
+        uint32_t pre_bit = 0;
+        if (taken && lane + L - 1 < 32) pre_bit = 1u << (lane + L - 1);
+        const uint32_t PRE = reduce_or(pre_bit);
+        const bool victim = ins && !((PRE >> lane) & 1u) && (same & C & ((1u << lane) - 1u)) != 0;
+        const uint32_t vm = ballot(victim);
+        if (vm) cut = ffs(vm) - 1;
+        // restore, then commit only the accepted prefix with "highest lane of a slot wins"
         syncwarp();
         if (ins) table[h] = (uint16_t)c;
         syncwarp();
-        return false;
+        const uint32_t keep = C & (cut >= 32 ? 0xFFFFFFFFu : ((1u << cut) - 1u));
+        if (((keep >> lane) & 1u) && (same & keep & ~((2u << lane) - 1u)) == 0) table[h] = (uint16_t)p;
+        syncwarp();
+        if (cut < 32) {
+            CS &= (1u << cut) - 1u;
+            const uint32_t ncut = popc(CS);
+            if (ncut) {
+                k1_wait_space(ring, head, ncut);
+                if ((CS >> lane) & 1u) ring.ev[(head.head + popc(CS & ((1u << lane) - 1u))) & (ring.size - 1)] = k1_event(p, L, p - c);
+                head.head += ncut;
+                if (head.head - head.published >= K1_PUBLISH) k1_publish(ring, head);
+                const unsigned lastc = 31 - clz(CS);
+                const uint32_t e2 = lastc + shfl(L, lastc);        // <= cut: the victim is not inside a copy
+                if (e2 == cut) { st.s = w + cut; st.rematch = true; }
+                else { st.s = w + cut; st.rematch = false; st.skip = 32 + (cut - e2 - 1); }
+            } else {
+                st.skip = st.rematch ? 32 + (cut - i0 - 1) : st.skip + (cut - i0);
+                st.s = w + cut; st.rematch = false;
+            }
+            return true;
+        }
     }
     // ---- publish the copies and leave the window
     const uint32_t ncopy = popc(CS);
@@ -478,7 +511,7 @@ SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, c
         const uint32_t m = avail < 32 ? avail : 32;
         threadfence_block();
         uint64_t ev = 0;
-        if (lane < m) ev = ring.ev[(tail + lane) & (ring.size - 1)];
+        if (lane < m) ev = ld_volatile64(&ring.ev[(tail + lane) & (ring.size - 1)]);   // the ring may live in global memory
         const uint32_t pos = (uint32_t)(ev & 0x1FFFFu), len = (uint32_t)((ev >> 17) & 0x1FFFFu), off = (uint32_t)(ev >> 34);
         const bool act = lane < m;
         const bool is_end = act && len == 0;
@@ -600,6 +633,64 @@ SB_DEVICE void k1_compress_body(const BatchDesc& b, uint32_t flags) {
             }
         } else {
             d = k1_emit_block(win, out, d, ring, tail);
+            if (lane == 0) b.out_lens[u] = d;
+        }
+    }
+}
+
+// One CTA per SM hosting NC independent (parser, emitter) warp pairs: NC hash tables fill the
+// SM's shared memory (7 x 32KB), the window is read in place from global memory and the event
+// rings live in an L2-resident global scratch (`ring_scratch`, K1_RING_GW entries per chain).
+// Pairs synchronise on their own named barrier, so chains never wait for each other.
+template <int NC>
+SB_DEVICE void k1_compress_body_multi(const BatchDesc& b, uint32_t flags, uint64_t* ring_scratch) {
+    uint8_t* sm = smem();
+    const unsigned lane = lane_id(), wid = warp_id();
+    const unsigned c = wid >> 1;                                       // chain within the CTA
+    const bool parser = (wid & 1u) == 0;
+    const unsigned pt = (wid & 1u) * 32 + lane;                        // thread index within the pair
+    const unsigned bar = 1 + c;
+    uint16_t* table = (uint16_t*)(sm + (size_t)c * K1_TABLE_BYTES);
+    uint32_t* ctrl = (uint32_t*)(sm + (size_t)NC * K1_TABLE_BYTES + c * 64);
+    const uint32_t g = block_idx() * NC + c, nchains = grid_dim() * NC;
+    K1Ring ring;
+    ring.size = K1_RING_GW;
+    ring.ev = ring_scratch + (size_t)g * K1_RING_GW;
+    ring.ctrl = ctrl;
+    uint32_t tail = 0;                // emitter's private ring counter (never reset)
+    if (pt == 0) { ctrl[0] = 0; ctrl[1] = 0; ctrl[6] = 0; ctrl[7] = 0; }
+    bar_sync(bar, 64);
+    for (uint32_t u = g; u < b.count; u += nchains) {
+        const uint8_t* in = unit_in(b, u);
+        const uint32_t n = unit_in_len(b, u);
+        uint8_t* out = unit_out(b, u);
+        uint32_t d = 0;
+        if (flags & 1u) {                                                  // varint header (:120-128)
+            if (n == 0) { if (pt == 0) { out[0] = 0; b.out_lens[u] = 1; } continue; }
+            uint32_t v = n;
+            while (v >= 0x80) { if (pt == 0) out[d] = (uint8_t)v | 0x80; v >>= 7; d++; }
+            if (pt == 0) out[d] = (uint8_t)v;
+            d++;
+        }
+        if (n == 0) { if (pt == 0) b.out_lens[u] = d; continue; }
+        bar_sync(bar, 64);                                                 // previous unit fully drained
+        {
+            uint32_t tsize = 256;
+            while (tsize < 16384 && tsize < n) tsize *= 2;
+            for (uint32_t i = pt; i < tsize / 2; i += 64) ((uint32_t*)table)[i] = 0;   // (:514-516)
+        }
+        bar_sync(bar, 64);
+        if (parser) {
+            if (n >= 17) k1_parse_pipelined<1>(in, n, table, ring, ctrl, 0);   // (:140-150)
+            else {                                                         // tiny block: one literal (:140-146)
+                K1Prod prod;
+                prod.head = ctrl[6]; prod.published = ctrl[7]; prod.tail_seen = 0;
+                k1_push(ring, prod, k1_event(n, 0, 0));
+                k1_publish(ring, prod);
+                if (lane == 0) { ctrl[6] = prod.head; ctrl[7] = prod.published; }
+            }
+        } else {
+            d = k1_emit_block(in, out, d, ring, tail);
             if (lane == 0) b.out_lens[u] = d;
         }
     }

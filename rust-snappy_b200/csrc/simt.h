@@ -69,6 +69,7 @@ SB_DEVICE void spin() { __nanosleep(32); }
 SB_DEVICE void spin_long() { __nanosleep(1500); }   // consumer side: latency does not matter, issue slots do
 SB_DEVICE uint32_t ld_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 SB_DEVICE void st_volatile(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
+SB_DEVICE uint64_t ld_volatile64(const uint64_t* p) { return *(const volatile uint64_t*)p; }
 
 // read-only / streaming global accessors
 SB_DEVICE uint32_t ldg32(const void* p) { return __ldg((const uint32_t*)p); }

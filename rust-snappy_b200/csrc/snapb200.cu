@@ -28,7 +28,10 @@ __global__ void __launch_bounds__(160) k1_s4_kernel(sb_batch b, uint32_t flags) 
 __global__ void __launch_bounds__(64) k1_g1_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<true, 1>(b, flags); }
 __global__ void __launch_bounds__(96) k1_g2_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<true, 2>(b, flags); }
 __global__ void __launch_bounds__(128) k1_g3_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<true, 3>(b, flags); }
+// one CTA per SM, 7 parser/emitter pairs, 7 tables in shared memory, rings in global scratch
+__global__ void __launch_bounds__(448, 1) k1_m7_kernel(sb_batch b, uint32_t flags, uint64_t* rings) { sbk::k1_compress_body_multi<7>(b, flags, rings); }
 __global__ void __launch_bounds__(128) k2_decompress_kernel(sb_batch b) { sbk::k2_decompress_body(b); }
+__global__ void __launch_bounds__(128, 16) k2_decompress_occ_kernel(sb_batch b) { sbk::k2_decompress_body(b); }
 __global__ void __launch_bounds__(256) k3_crc_kernel(sb_batch b) { sbk::k3_crc_body(b); }
 __global__ void __launch_bounds__(256) k4_sizes_kernel(sbk::FramePlan p) { sbk::k4_sizes_body(p); }
 __global__ void __launch_bounds__(1024) k4_scan_kernel(sbk::FramePlan p) { sbk::k4_scan_body(p); }
@@ -39,6 +42,7 @@ __global__ void __launch_bounds__(256) k6_generate_kernel(sbk::GenPlan g) { sbk:
 std::atomic<uint64_t> g_launches{0};
 const int K1_DEFAULT_NP = 1;
 const int K1_DEFAULT_GW = 1;
+const int K1_DEFAULT_MULTI = 1;
 
 int fail(sb_error* e, uint32_t code, uint64_t a = 0, uint64_t b = 0, uint64_t c = 0) {
     if (e) { e->code = code; e->_pad = 0; e->a = a; e->b = b; e->c = c; }
@@ -77,6 +81,7 @@ struct Ctx {
     int dev = -1, sms = 0;
     bool ready = false;
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    DevBuf rings;
     DevBuf in[2], slots[2], compact[2], lens[2], csize[2], offs[2], crcs[2], status[2], ptrs_in[2], ptrs_out[2], caps[2];
     void* pinned = nullptr; size_t pinned_cap = 0;
     std::mutex mu;
@@ -99,6 +104,8 @@ int get_ctx(Ctx** out, sb_error* err) {
         CK(cudaFuncSetAttribute(k1_g1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
         CK(cudaFuncSetAttribute(k1_g2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
         CK(cudaFuncSetAttribute(k1_g3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
+        CK(cudaFuncSetAttribute(k1_m7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(7 * sbk::K1_TABLE_BYTES + 7 * 64)));
+        CK(c.rings.need((size_t)c.sms * 7 * sbk::K1_RING_GW * 8));
         CK(cudaStreamCreateWithFlags(&c.s_compute, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking));
@@ -126,7 +133,12 @@ int launch_k1(Ctx& c, const sb_batch& b, uint32_t flags, cudaStream_t st, sb_err
     unsigned grid = (unsigned)((gw ? 6 : 2) * c.sms);
     if (grid > b.count) grid = b.count;
     const size_t sm = gw ? sbk::K1_SMEM_BYTES_GW : sbk::K1_SMEM_BYTES;
-    if (gw) {
+    static const int multi = getenv("SNAPB200_K1_MULTI") ? atoi(getenv("SNAPB200_K1_MULTI")) : K1_DEFAULT_MULTI;
+    if (multi) {
+        unsigned mg = (unsigned)c.sms;
+        if ((uint64_t)mg * 7 > b.count) mg = (unsigned)((b.count + 6) / 7);
+        k1_m7_kernel<<<mg, 448, 7 * sbk::K1_TABLE_BYTES + 7 * 64, st>>>(b, flags, c.rings.as<uint64_t>());
+    } else if (gw) {
         if (np <= 1) k1_g1_kernel<<<grid, 64, sm, st>>>(b, flags);
         else if (np == 2) k1_g2_kernel<<<grid, 96, sm, st>>>(b, flags);
         else k1_g3_kernel<<<grid, 128, sm, st>>>(b, flags);
@@ -146,7 +158,9 @@ int launch_k2(Ctx& c, const sb_batch& b, cudaStream_t st, sb_error* err) {
     uint64_t blocks = ((uint64_t)b.count + wpb - 1) / wpb;
     unsigned grid = (unsigned)(16 * c.sms);
     if (grid > blocks) grid = (unsigned)blocks;
-    k2_decompress_kernel<<<grid, 32 * wpb, 0, st>>>(b);
+    static const int occ = getenv("SNAPB200_K2_OCC") ? atoi(getenv("SNAPB200_K2_OCC")) : 0;
+    if (occ) k2_decompress_occ_kernel<<<grid, 32 * wpb, 0, st>>>(b);
+    else k2_decompress_kernel<<<grid, 32 * wpb, 0, st>>>(b);
     g_launches++;
     CK(cudaGetLastError());
     return 0;

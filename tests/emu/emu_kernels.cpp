@@ -5,9 +5,10 @@
 #include "../../rust-snappy_b200/csrc/k1_compress.cuh"
 #include "../../rust-snappy_b200/csrc/k2_decompress.cuh"
 
-struct K1Args { sb_batch b; uint32_t flags; };
+struct K1Args { sb_batch b; uint32_t flags; uint64_t* rings; };
 static void k1_entry(void* a) {
     K1Args* x = (K1Args*)a;
+    if (x->flags & 0x200u) { sbk::k1_compress_body_multi<7>(x->b, x->flags & 0xFFu, x->rings); return; }
     const bool gw = x->flags & 0x100u;
     const unsigned np = (x->flags >> 12) & 7u, f = x->flags & 0xFFu;
     if (gw) { if (np <= 1) sbk::k1_compress_body<true, 1>(x->b, f); else if (np == 2) sbk::k1_compress_body<true, 2>(x->b, f); else sbk::k1_compress_body<true, 3>(x->b, f); }
@@ -18,7 +19,13 @@ static void k2_entry(void* a) { sbk::k2_decompress_body(*(sb_batch*)a); }
 extern "C" {
 
 int emu_compress_batch(const sb_batch* b, uint32_t flags, unsigned grid) {
-    K1Args a{*b, flags};
+    K1Args a{*b, flags, nullptr};
+    if (flags & 0x200u) {
+        std::vector<uint64_t> rings((size_t)grid * 7 * sbk::K1_RING_GW, 0xCDCDCDCDCDCDCDCDull);
+        a.rings = rings.data();
+        sbemu::launch(grid, 448, 7 * sbk::K1_TABLE_BYTES + 7 * 64, k1_entry, &a);
+        return 0;
+    }
     const unsigned np = (flags >> 12) & 7u;
     sbemu::launch(grid, ((np < 1 ? 1 : np > 3 ? 3 : np) + 1) * 32, sbk::K1_SMEM_BYTES, k1_entry, &a);
     return 0;
