@@ -19,6 +19,8 @@
 
 namespace sbk {
 
+static const uint32_t K2_SMEM_PER_WARP = 256;   // bytes of shared scratch per warp
+
 // varint header: reference src/bytes.rs:73-90 + src/decompress.rs:362-374
 // returns header length (0 = malformed) -- executed redundantly by all lanes.
 SB_DEVICE uint32_t k2_read_header(const uint8_t* in, uint32_t n, uint64_t* value) {
@@ -36,7 +38,7 @@ SB_DEVICE uint32_t k2_read_header(const uint8_t* in, uint32_t n, uint64_t* value
 
 // Decode one raw stream with the calling warp. Returns the status code.
 SB_DEVICE uint32_t k2_decode_stream(const uint8_t* in, uint32_t n, uint8_t* dst, uint64_t cap,
-                                    sb_error* st, uint32_t* out_len) {
+                                    sb_error* st, uint32_t* out_len, uint32_t* elems) {
     const unsigned lane = lane_id();
     if (n == 0) { if (lane == 0) set_status(st, SB_EMPTY, 0, 0, 0); return SB_EMPTY; }
     uint64_t dn64 = 0;
@@ -168,32 +170,57 @@ SB_DEVICE uint32_t k2_decode_stream(const uint8_t* in, uint32_t n, uint8_t* dst,
         syncwarp();
 
         // ---- copies. A copy whose source lies entirely before this window's output
-        // (offset >= opos + len) depends on nothing written in this window: those are
-        // issued four at a time, loads first, so their L2 round trips overlap. The rest
-        // (recent/overlapping sources, lengths above 32) are replayed one by one in stream order.
+        // (offset >= opos + len) depends on nothing written in this window. Those are flattened:
+        // their bytes form one compact index space, one lane per copied byte, so a window's
+        // ~30-60 copied bytes move in one or two warp-wide load/store pairs regardless of how many
+        // copies they belong to. The rest (recent/overlapping sources, lengths above 32) are
+        // replayed one by one in stream order afterwards.
         {
             uint8_t* const wout = dst + d;                       // window output base
             const uint32_t cpk = opos | ((uint32_t)len << 12);   // len <= 64 for copies, opos <= 2048
             const bool is_copy = is_start && kind != 0;
             const bool indep = is_copy && (uint32_t)len <= 32 && off >= opos + (uint32_t)len;
-            uint32_t ic = ballot(indep);
-            while (ic) {
-                uint32_t pk[4], co[4];
-                uint8_t v[4];
+            const uint32_t im = ballot(indep);
+            if (im) {
+                // compact index of my first byte = prefix sum of independent copy lengths
+                const uint32_t ilen = indep ? (uint32_t)len : 0u;
+                uint32_t cincl = ilen;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const unsigned j = ic ? ffs(ic) - 1 : 0;
-                    const bool on = ic != 0;
-                    ic &= ic - 1;
-                    pk[q] = shfl(cpk, j); co[q] = shfl(off, j);
-                    if (!on) pk[q] = 0;                          // length 0: nothing to do
+                for (int k = 1; k < 32; k <<= 1) {
+                    const uint32_t t2 = shfl_up(cincl, k);
+                    if (lane >= (unsigned)k) cincl += t2;
                 }
+                const uint32_t cpos = cincl - ilen, ctot = shfl(cincl, 31);
+                // element table in shared memory, indexed by rank among the independent copies
+                if (indep) {
+                    const uint32_t rk = popc(im & ((1u << lane) - 1u));
+                    elems[rk * 2] = cpk | (cpos << 20);          // opos:12 | len:8 | cpos:12
+                    elems[rk * 2 + 1] = off;
+                }
+                syncwarp();
+                for (uint32_t base = 0; base < ctot; base += 64) {
+                    uint32_t dsto[2], srco[2];
+                    uint8_t v[2];
+                    bool on[2];
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    v[q] = lane < (pk[q] >> 12) ? (wout + (pk[q] & 0xFFFu))[(int)lane - (int)co[q]] : (uint8_t)0;
+                    for (int q = 0; q < 2; q++) {
+                        const uint32_t lo = base + 32 * q;
+                        // starts inside [lo, lo+32) -> bit; owner rank of byte t = starts at or before t, minus one
+                        const uint32_t bit = (indep && cpos >= lo && cpos < lo + 32) ? 1u << (cpos - lo) : 0u;
+                        const uint32_t Bm = reduce_or(bit);
+                        const uint32_t before = popc(ballot(indep && cpos < lo));
+                        const uint32_t t = lo + lane;
+                        on[q] = t < ctot;
+                        const uint32_t rk = before + popc(Bm & (0xFFFFFFFFu >> (31 - lane))) - 1;
+                        const uint32_t e0 = on[q] ? elems[rk * 2] : 0u, e1 = on[q] ? elems[rk * 2 + 1] : 0u;
+                        dsto[q] = (e0 & 0xFFFu) + (t - (e0 >> 20));
+                        srco[q] = e1;
+                    }
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (lane < (pk[q] >> 12)) (wout + (pk[q] & 0xFFFu))[lane] = v[q];
+                    for (int q = 0; q < 2; q++) v[q] = on[q] ? wout[(int)dsto[q] - (int)srco[q]] : (uint8_t)0;
+#pragma unroll
+                    for (int q = 0; q < 2; q++) if (on[q]) wout[dsto[q]] = v[q];
+                }
             }
             syncwarp();
             uint32_t cm = ballot(is_copy && !indep);
@@ -241,12 +268,13 @@ SB_DEVICE uint32_t k2_decode_stream(const uint8_t* in, uint32_t n, uint8_t* dst,
 // Kernel body: warp w of the grid decodes units w, w+nwarps, ...
 SB_DEVICE void k2_decompress_body(const BatchDesc& b) {
     const unsigned warps_per_block = block_dim() >> 5;
+    uint32_t* elems = (uint32_t*)smem() + warp_id() * 64;           // per-warp scratch: 32 x (packed element, offset)
     const uint64_t nwarps = (uint64_t)grid_dim() * warps_per_block;
     for (uint64_t u = (uint64_t)block_idx() * warps_per_block + warp_id(); u < b.count; u += nwarps) {
         const uint32_t i = (uint32_t)u;
         if (b.out_lens && lane_id() == 0) b.out_lens[i] = 0;
         k2_decode_stream(unit_in(b, i), unit_in_len(b, i), unit_out(b, i), unit_out_cap(b, i),
-                         b.statuses ? &b.statuses[i] : nullptr, b.out_lens ? &b.out_lens[i] : nullptr);
+                         b.statuses ? &b.statuses[i] : nullptr, b.out_lens ? &b.out_lens[i] : nullptr, elems);
     }
 }
 

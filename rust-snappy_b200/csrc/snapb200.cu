@@ -31,7 +31,6 @@ __global__ void __launch_bounds__(128) k1_g3_kernel(sb_batch b, uint32_t flags) 
 // one CTA per SM, 7 parser/emitter pairs, 7 tables in shared memory, rings in global scratch
 __global__ void __launch_bounds__(448, 1) k1_m7_kernel(sb_batch b, uint32_t flags, uint64_t* rings) { sbk::k1_compress_body_multi<7>(b, flags, rings); }
 __global__ void __launch_bounds__(128) k2_decompress_kernel(sb_batch b) { sbk::k2_decompress_body(b); }
-__global__ void __launch_bounds__(128, 16) k2_decompress_occ_kernel(sb_batch b) { sbk::k2_decompress_body(b); }
 __global__ void __launch_bounds__(256) k3_crc_kernel(sb_batch b) { sbk::k3_crc_body(b); }
 __global__ void __launch_bounds__(256) k4_sizes_kernel(sbk::FramePlan p) { sbk::k4_sizes_body(p); }
 __global__ void __launch_bounds__(1024) k4_scan_kernel(sbk::FramePlan p) { sbk::k4_scan_body(p); }
@@ -158,9 +157,7 @@ int launch_k2(Ctx& c, const sb_batch& b, cudaStream_t st, sb_error* err) {
     uint64_t blocks = ((uint64_t)b.count + wpb - 1) / wpb;
     unsigned grid = (unsigned)(16 * c.sms);
     if (grid > blocks) grid = (unsigned)blocks;
-    static const int occ = getenv("SNAPB200_K2_OCC") ? atoi(getenv("SNAPB200_K2_OCC")) : 0;
-    if (occ) k2_decompress_occ_kernel<<<grid, 32 * wpb, 0, st>>>(b);
-    else k2_decompress_kernel<<<grid, 32 * wpb, 0, st>>>(b);
+    k2_decompress_kernel<<<grid, 32 * wpb, wpb * sbk::K2_SMEM_PER_WARP, st>>>(b);
     g_launches++;
     CK(cudaGetLastError());
     return 0;

@@ -33,7 +33,7 @@ int emu_compress_batch(const sb_batch* b, uint32_t flags, unsigned grid) {
 
 int emu_decompress_batch(const sb_batch* b, unsigned grid, unsigned block) {
     sb_batch c = *b;
-    sbemu::launch(grid, block, 0, k2_entry, &c);
+    sbemu::launch(grid, block, (block / 32) * sbk::K2_SMEM_PER_WARP, k2_entry, &c);
     return 0;
 }
 
