@@ -403,6 +403,71 @@ def run_e2e(args, snap, L, torch, dev, t_in, t_clen, rank, world):
             "ms_per_step": 1e3 * dt / args.steps}
 
 
+def run_urls(args, local_rank):
+    """BASELINE configs[2]: urls.10K cut into 11 blocks, each compressed independently, tiled
+    round-robin (compressed bytes physically replicated in HBM) and decoded by K2."""
+    import numpy as np
+    import torch
+    import __graft_entry__ as graft
+    from oracle import oracle as orc
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    snap = graft.load_package()
+    L = snap._lib.lib()
+    err = snap._lib.SbError()
+    data = open(os.path.join(ROOT, "tests", "golden", "data", "urls.10K"), "rb").read()
+    blocks = [data[i:i + BLOCK] for i in range(0, len(data), BLOCK)]
+    comp = [orc.compress(b) for b in blocks]                  # input preparation, outside the timed region
+    reps = int(args.urls_gib * (1 << 30)) // len(data)
+    n = reps * len(blocks)
+    clen = np.array([len(c) for c in comp], dtype=np.int64)
+    tile = int(clen.sum())
+    src = torch.frombuffer(bytearray(b"".join(comp)), dtype=torch.uint8).to(dev)
+    t_c = src.repeat(reps)                                    # physical tiling of the compressed streams
+    starts = np.concatenate([[0], np.cumsum(clen)[:-1]])
+    base = (np.arange(reps, dtype=np.int64) * tile)[:, None] + starts[None, :]
+    in_ptrs = torch.from_numpy(base.reshape(-1) + t_c.data_ptr()).to(dev)
+    in_lens = torch.from_numpy(np.tile(clen, reps).astype(np.int32)).to(dev)
+    t_out = torch.empty(n * BLOCK, dtype=torch.uint8, device=dev)
+    t_dlen = torch.zeros(n, dtype=torch.int32, device=dev)
+    t_st = torch.zeros(n * 4, dtype=torch.int64, device=dev)
+    b = snap._lib.SbBatch()
+    b.in_ptrs, b.in_lens = in_ptrs.data_ptr(), in_lens.data_ptr()
+    b.out_base, b.out_stride, b.out_cap_uniform = t_out.data_ptr(), BLOCK, BLOCK
+    b.out_lens, b.statuses, b.count = t_dlen.data_ptr(), t_st.data_ptr(), n
+    stream = torch.cuda.current_stream().cuda_stream
+    ev = torch.cuda.Event
+
+    def step():
+        e0, e1 = ev(enable_timing=True), ev(enable_timing=True)
+        e0.record()
+        if L.sb_decompress_batch_device(C.byref(b), stream, C.byref(err)):
+            raise snap.error.from_c(err)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    assert int(t_st.view(n, 4)[:, 0].abs().sum()) == 0
+    view = t_out.view(reps, len(blocks), BLOCK)
+    for k, blk in enumerate(blocks):                          # every tile decodes to the original bytes
+        want = torch.frombuffer(bytearray(blk), dtype=torch.uint8).to(dev)
+        assert bool((view[:, k, :len(blk)] == want).all())
+    ms = sum(step() for _ in range(args.steps)) / args.steps
+    u, c = reps * len(data), reps * tile
+    peak, peak_src = measured_peak()
+    print(json.dumps({
+        "metric": "uncompressed GB/s, batched raw block decompress", "value": u / (ms / 1e3) / 1e9, "unit": "GB/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+        "dtype": "u8", "data": "data/urls.10K tiled", "side_measurement": True,
+        "config": {"workload": "batched raw block decompress: data/urls.10K tiled to %.1f GiB (BASELINE configs[2])" % (u / 2**30),
+                   "streams": n, "compressed_bytes": c, "ratio": c / u, "parity": "every stream equals its source block"},
+        "roofline": {"bound": "hbm", "kernel": "k2_decompress_kernel", "achieved": (u + c) / (ms / 1e3) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": (u + c) / (ms / 1e3) / 1e9 / peak, "peak_source": peak_src, "traffic": None},
+    }), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -416,6 +481,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="text-roundtrip", choices=["text-roundtrip", "urls-decompress"],
+                    help="urls-decompress = BASELINE configs[2] (data/urls.10K tiled), decompress only; a side measurement")
+    ap.add_argument("--urls-gib", type=float, default=64.0)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -424,6 +492,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "urls-decompress":
+        run_urls(args, local_rank)
         return
     run_ours(args, rank, local_rank, world)
     if world > 1:

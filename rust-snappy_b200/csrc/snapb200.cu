@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) k6_generate_kernel(sbk::GenPlan g) { sbk:
 
 std::atomic<uint64_t> g_launches{0};
 const int K1_DEFAULT_NP = 1;
+const int K2_DEFAULT_CTAS_PER_SM = 16;
 const int K1_DEFAULT_GW = 1;
 const int K1_DEFAULT_MULTI = 1;
 
@@ -155,7 +156,10 @@ int launch_k2(Ctx& c, const sb_batch& b, cudaStream_t st, sb_error* err) {
     if (b.count == 0) return 0;
     const unsigned wpb = 4;
     uint64_t blocks = ((uint64_t)b.count + wpb - 1) / wpb;
-    unsigned grid = (unsigned)(16 * c.sms);
+    // resident CTAs per SM: each warp keeps a 64KB output history alive, and copy sources are
+    // re-read from it -- too many streams in flight and the history falls out of the 126MB L2
+    static const int per_sm = getenv("SNAPB200_K2_CTAS") ? atoi(getenv("SNAPB200_K2_CTAS")) : K2_DEFAULT_CTAS_PER_SM;
+    unsigned grid = (unsigned)(per_sm * c.sms);
     if (grid > blocks) grid = (unsigned)blocks;
     k2_decompress_kernel<<<grid, 32 * wpb, wpb * sbk::K2_SMEM_PER_WARP, st>>>(b);
     g_launches++;

@@ -331,3 +331,40 @@ def test_libsnappy_compatible_symbols(snap, oracle):
     assert L.snappy_compress(data, len(data), buf, C.byref(small)) == 2          # SNAPPY_BUFFER_TOO_SMALL
     bad, k2 = b"\x05\x00a", C.c_size_t(16)
     assert L.snappy_uncompress(bad, 3, out, C.byref(k2)) == 1                      # SNAPPY_INVALID_INPUT
+
+
+def test_config3_urls_tiled_decompress(snap, oracle):
+    """BASELINE configs[2] shape at test scale: data/urls.10K cut into 11 blocks, each compressed
+    independently (oracle), tiled round-robin into 22000 streams, decoded by the batched kernel."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import gpu_helpers
+    L = gpu_helpers.lib()
+    data = corpus("urls.10K")
+    blocks = [data[i:i + 65536] for i in range(0, len(data), 65536)]
+    comp = [oracle.compress(b) for b in blocks]
+    assert [len(c) for c in comp] == [31817, 30911, 30063, 30746, 30054, 31451, 32143, 32131, 32204, 31097, 22905]  # SURVEY 8d
+    reps = 2000
+    n = len(blocks) * reps
+    dev = torch.device("cuda:0")
+    src = torch.frombuffer(bytearray(b"".join(comp)), dtype=torch.uint8).to(dev)
+    coff = np.concatenate([[0], np.cumsum([len(c) for c in comp])[:-1]])
+    in_ptrs = torch.tensor([src.data_ptr() + int(coff[i % 11]) for i in range(n)], dtype=torch.int64, device=dev)
+    in_lens = torch.tensor([len(comp[i % 11]) for i in range(n)], dtype=torch.int32, device=dev)
+    out = torch.zeros(n * 65536, dtype=torch.uint8, device=dev)
+    dlen = torch.zeros(n, dtype=torch.int32, device=dev)
+    st = torch.zeros(n * 4, dtype=torch.int64, device=dev)
+    b = snap._lib.SbBatch()
+    b.in_ptrs, b.in_lens = in_ptrs.data_ptr(), in_lens.data_ptr()
+    b.out_base, b.out_stride, b.out_cap_uniform = out.data_ptr(), 65536, 65536
+    b.out_lens, b.statuses, b.count = dlen.data_ptr(), st.data_ptr(), n
+    e = snap._lib.SbError()
+    assert L.sb_decompress_batch_device(C.byref(b), torch.cuda.current_stream().cuda_stream, C.byref(e)) == 0
+    torch.cuda.synchronize()
+    assert int(st.view(n, 4)[:, 0].abs().sum()) == 0
+    view = out.view(reps, 11, 65536)
+    for k, blk in enumerate(blocks):
+        want = torch.frombuffer(bytearray(blk), dtype=torch.uint8).to(dev)
+        assert bool((view[:, k, :len(blk)] == want).all())
+        assert bool((dlen.view(reps, 11)[:, k] == len(blk)).all())
