@@ -120,9 +120,7 @@ SB_DEVICE uint32_t k1_extend(const uint8_t* win, uint32_t n, uint32_t s, uint32_
 struct K1State {
     uint32_t s;        // next event position
     uint32_t skip;     // scan state (src/compress.rs:204-211); meaningful when !rematch
-    bool rematch;      // true: a copy just ended at s (:285-301)
-    bool pend;         // rematch only: the copy-end insert of s-1 (:293-295) is still owed; it is folded
-                       // into the next window's commit instead of paying a global load for it now
+    bool rematch;      // true: a copy just ended at s and s-1 is already inserted (:285-301 first half)
 };
 
 #define K1_HASH(x) (((uint32_t)(x) * 0x1E35A7BDu) >> shift)
@@ -147,8 +145,7 @@ SB_DEVICE bool k1_serial(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         uint32_t cand;
         if (st.rematch) {
             if (st.s >= s_limit) return true;
-            if (st.pend) { k1_preinsert(win, table, shift, s_limit, st.s); st.pend = false; }
-            // probe at s (:296-313); s-1 is inserted by now
+            // probe at s (:296-313); s-1 was inserted when the copy ended
             const uint32_t cur = k1_rd32(win, st.s);
             const uint32_t h = K1_HASH(cur);
             cand = table[h];
@@ -156,7 +153,7 @@ SB_DEVICE bool k1_serial(const uint8_t* win, uint32_t n, uint16_t* table, unsign
             if (lane == 0) table[h] = (uint16_t)st.s;
             syncwarp();
             if (cur != k1_rd32(win, cand)) {
-                st.s += 1; st.rematch = false; st.pend = false; st.skip = 32;
+                st.s += 1; st.rematch = false; st.skip = 32;
                 if (st.s >= target) return false;
                 continue;
             }
@@ -201,7 +198,7 @@ SB_DEVICE bool k1_serial(const uint8_t* win, uint32_t n, uint16_t* table, unsign
 #endif
         k1_push(ring, head, k1_event(base, end - base, base - cand));
         k1_preinsert(win, table, shift, s_limit, end);
-        st.s = end; st.rematch = true; st.pend = false;
+        st.s = end; st.rematch = true;
         if (st.s >= target) return false;
     }
 }
@@ -242,7 +239,6 @@ SB_DEVICE uint32_t k1_double(uint32_t E, bool eq, uint32_t L) {
     for (int r = 0; r < 5; r++) {
         const uint32_t M2 = shfl(M, T & 31u), T2 = shfl(T, T & 31u);
         if (T < 32) { M |= M2; T = T2; }
-        if (r == 2 && !any(T < 32)) break;                // 8 hops cover almost every window
     }
     return M;
 }
@@ -322,8 +318,7 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         interior = upto & ~((1u << lo) - 1u);
     }
     const uint32_t I = reduce_or(interior);
-    const uint32_t owed = (st.rematch && st.pend) ? 1u : 0u;      // lane i0-1 = position s-1 (caller guarantees i0 >= 1)
-    const uint32_t C = (0xFFFFFFFFu << (i0 - owed)) & ~I;
+    const uint32_t C = (0xFFFFFFFFu << i0) & ~I;
     const bool ins = (C >> lane) & 1u;
 #ifdef SB_EMU_TRACE
     if (lane == 0) fprintf(stderr, "win w=%u i0=%u rm=%d skip=%u E=%08x f=%u CS=%08x C=%08x\n", w, i0, (int)st.rematch, st.skip, E, f, CS, C);
@@ -340,7 +335,7 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         const uint32_t same = match_any(ins ? h : 0xFFFF0000u | lane);
         uint32_t pre_bit = 0;
         if (taken && lane + L - 1 < 32) pre_bit = 1u << (lane + L - 1);
-        const uint32_t PRE = reduce_or(pre_bit) | (owed ? 1u << (i0 - 1) : 0u);
+        const uint32_t PRE = reduce_or(pre_bit);
         const bool victim = ins && !((PRE >> lane) & 1u) && (same & C & ((1u << lane) - 1u)) != 0;
         const uint32_t vm = ballot(victim);
         if (vm) cut = ffs(vm) - 1;
@@ -363,10 +358,9 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
                 const uint32_t e2 = lastc + shfl(L, lastc);        // <= cut: the victim is not inside a copy
                 if (e2 == cut) { st.s = w + cut; st.rematch = true; }
                 else { st.s = w + cut; st.rematch = false; st.skip = 32 + (cut - e2 - 1); }
-                st.pend = false;
             } else {
                 st.skip = st.rematch ? 32 + (cut - i0 - 1) : st.skip + (cut - i0);
-                st.s = w + cut; st.rematch = false; st.pend = false;
+                st.s = w + cut; st.rematch = false;
             }
             return true;
         }
@@ -382,13 +376,13 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         const uint32_t e_last = last + shfl(L, last);
         if (e_last >= 32) {
             st.s = w + e_last; st.rematch = true;
-            st.pend = e_last >= 33;                               // e-1 lies beyond this window: owed to the next one
+            if (e_last >= 33) k1_preinsert(win, table, shift, s_limit, st.s);   // e-1 lies beyond this window
         } else {
-            st.s = w + 32; st.rematch = false; st.pend = false; st.skip = 32 + (31 - e_last);
+            st.s = w + 32; st.rematch = false; st.skip = 32 + (31 - e_last);
         }
     } else {
         st.skip = st.rematch ? 32 + (31 - i0) : st.skip + (32 - i0);
-        st.s = w + 32; st.rematch = false; st.pend = false;
+        st.s = w + 32; st.rematch = false;
     }
     return true;
 }
@@ -425,7 +419,7 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
     seq.a0 = seq.a1 = seq.a2 = seq.a3 = 0; seq.w = 0xFFFFFFFFu;
     uint32_t my = k;
     K1State lst;                                                   // NP == 1: parse state kept in registers
-    lst.s = 1; lst.skip = 32; lst.rematch = false; lst.pend = false;
+    lst.s = 1; lst.skip = 32; lst.rematch = false;
     bool first = (k == 0);                                         // warp 0 starts with the token
     for (;;) {
         // probe ahead (stale table) while the token is elsewhere
@@ -439,7 +433,7 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
         K1State st;
         if (NP == 1) {
             // single parser: state lives in registers, only the producer counters persist across units
-            if (my == 0) { lst.s = 1; lst.skip = 32; lst.rematch = false; lst.pend = false; prod.head = ld_volatile(&ctrl[6]); prod.published = ld_volatile(&ctrl[7]); }
+            if (my == 0) { lst.s = 1; lst.skip = 32; lst.rematch = false; prod.head = ld_volatile(&ctrl[6]); prod.published = ld_volatile(&ctrl[7]); }
             st = lst;
             my = st.s >> 5; w = my * 32;
         } else {
@@ -449,18 +443,13 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
                 if (t % NP != k) { bar_arrive(bar_next, 64); continue; }   // not mine: forward the token
                 my = t; w = my * 32; have = false;                 // jumped ahead to a window of mine
             }
-            st.s = ld_volatile(&ctrl[3]); st.skip = ld_volatile(&ctrl[4]); st.rematch = (ld_volatile(&ctrl[5]) & 1u) != 0; st.pend = (ld_volatile(&ctrl[5]) & 2u) != 0;
+            st.s = ld_volatile(&ctrl[3]); st.skip = ld_volatile(&ctrl[4]); st.rematch = ld_volatile(&ctrl[5]) != 0;
             prod.head = ld_volatile(&ctrl[6]); prod.published = ld_volatile(&ctrl[7]);
         }
         bool finished;
         if (st.rematch ? st.s >= s_limit : st.s + (st.skip >> 5) > s_limit) finished = true;
         else {
             bool ok = false;
-            if (st.rematch && st.pend && (st.s & 31u) == 0) {      // s-1 is not in this window: settle it now
-                k1_preinsert(win, table, shift, s_limit, st.s);
-                st.pend = false;
-                have = false;
-            }
             if (w + 32 < s_limit && (st.rematch || st.skip < 64)) {
                 if (have) {
                     const uint32_t cn = table[pre.h];
@@ -492,7 +481,7 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
         }
         syncwarp();
         if (lane == 0) {
-            ctrl[3] = st.s; ctrl[4] = st.skip; ctrl[5] = (st.rematch ? 1u : 0u) | (st.pend ? 2u : 0u);
+            ctrl[3] = st.s; ctrl[4] = st.skip; ctrl[5] = st.rematch ? 1u : 0u;
             ctrl[6] = prod.head; ctrl[7] = prod.published;
             ctrl[2] = finished ? K1_DONE : (st.s >> 5);
         }
