@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 #include <vector>
+#include <time.h>
 
 #include "k1_compress.cuh"
 #include "k2_decompress.cuh"
@@ -83,7 +84,7 @@ struct Ctx {
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     DevBuf rings;
     DevBuf in[2], slots[2], compact[2], lens[2], csize[2], offs[2], crcs[2], status[2], ptrs_in[2], ptrs_out[2], caps[2];
-    void* pinned = nullptr; size_t pinned_cap = 0;
+    void* pinned[4] = {nullptr, nullptr, nullptr, nullptr}; size_t pinned_cap[4] = {0, 0, 0, 0};   // pinned staging: [0,1] descriptors in, [2,3] results out
     std::mutex mu;
 };
 Ctx g_ctx[16];
@@ -115,11 +116,14 @@ int get_ctx(Ctx** out, sb_error* err) {
     return 0;
 }
 
-int need_pinned(Ctx& c, size_t n, sb_error* err) {
-    if (n <= c.pinned_cap) return 0;
-    if (c.pinned) { CK(cudaFreeHost(c.pinned)); c.pinned = nullptr; c.pinned_cap = 0; }
-    CK(cudaHostAlloc(&c.pinned, n, cudaHostAllocDefault));
-    c.pinned_cap = n;
+// Descriptor arrays (pointers, lengths) are staged through pinned memory: an async copy from
+// pageable memory would not overlap with the running kernel.
+int need_pinned(Ctx& c, int slot, size_t n, sb_error* err) {
+    if (n <= c.pinned_cap[slot]) return 0;
+    if (c.pinned[slot]) { CK(cudaFreeHost(c.pinned[slot])); c.pinned[slot] = nullptr; c.pinned_cap[slot] = 0; }
+    n += n / 4 + 4096;
+    CK(cudaHostAlloc(&c.pinned[slot], n, cudaHostAllocDefault));
+    c.pinned_cap[slot] = n;
     return 0;
 }
 
@@ -515,30 +519,47 @@ int sb_compress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, cons
             at += (run + 15) & ~(uint64_t)15;
             i = j;
         }
-        std::vector<uint64_t> ptrs(w.count);
+        { int prc = need_pinned(*c, b, w.count * 12 + 64, err); if (prc) return prc; }
+        uint64_t* ptrs = (uint64_t*)c->pinned[b];
+        uint32_t* plen = (uint32_t*)(ptrs + w.count);
         for (size_t k = 0; k < w.count; k++) ptrs[k] = (uint64_t)(uintptr_t)(c->in[b].as<uint8_t>() + doff[k]);
-        CK(cudaMemcpyAsync(c->ptrs_in[b].p, ptrs.data(), w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
-        CK(cudaMemcpyAsync(c->caps[b].p, in_lens + w.first, w.count * 4, cudaMemcpyHostToDevice, c->s_h2d));
+        memcpy(plen, in_lens + w.first, w.count * 4);
+        CK(cudaMemcpyAsync(c->ptrs_in[b].p, ptrs, w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
+        CK(cudaMemcpyAsync(c->caps[b].p, plen, w.count * 4, cudaMemcpyHostToDevice, c->s_h2d));
         CK(cudaStreamSynchronize(c->s_h2d));   // host temporaries + simple ordering; copies of the NEXT wave overlap kernels
         CK(cudaEventRecord(ev_in[b], c->s_h2d));
         return 0;
     };
+    const bool timing = getenv("SNAPB200_TIMING") != nullptr;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_begin = now_ms();
     if (!waves.empty()) { rc = stage_in(0); if (rc) return rc; }
     for (size_t wi = 0; wi < waves.size(); wi++) {
         const Wave& w = waves[wi];
         const int b = (int)(wi & 1);
+        if (timing) fprintf(stderr, "[compress wave %zu] t=%.2f launch (count %zu)\n", wi, now_ms() - t_begin, w.count);
         CK(cudaStreamWaitEvent(c->s_compute, ev_in[b], 0));
+        if (wi >= 2) CK(cudaStreamWaitEvent(c->s_compute, ev_out[b], 0));   // wave wi-2 (same buffers) fully drained
         sb_batch bt;
         memset(&bt, 0, sizeof bt);
         bt.in_ptrs = (const uint8_t* const*)c->ptrs_in[b].p; bt.in_lens = c->caps[b].as<uint32_t>();
         bt.out_base = c->slots[b].as<uint8_t>(); bt.out_stride = sbk::kSlotStride; bt.out_cap_uniform = sbk::kSlotStride;
         bt.out_lens = c->lens[b].as<uint32_t>(); bt.count = (uint32_t)w.count;
+        cudaEvent_t tk0 = nullptr, tk1 = nullptr;
+        if (timing) { cudaEventCreate(&tk0); cudaEventCreate(&tk1); cudaEventRecord(tk0, c->s_compute); }
         rc = launch_k1(*c, bt, 1u, c->s_compute, err);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(out_lens + w.first, c->lens[b].p, w.count * 4, cudaMemcpyDeviceToHost, c->s_compute));
+        if (timing) cudaEventRecord(tk1, c->s_compute);
+        // results come back through pinned staging: a D2H copy into the caller's (pageable) array
+        // would block this thread until the kernel is done and serialise the next wave's H2D behind it
+        { int prc = need_pinned(*c, 2 + b, w.count * 4 + 64, err); if (prc) return prc; }
+        CK(cudaMemcpyAsync(c->pinned[2 + b], c->lens[b].p, w.count * 4, cudaMemcpyDeviceToHost, c->s_compute));
         CK(cudaEventRecord(ev_k[b], c->s_compute));
         if (wi + 1 < waves.size()) { rc = stage_in(wi + 1); if (rc) return rc; }   // overlaps the kernel above
+        if (timing) fprintf(stderr, "[compress wave %zu] t=%.2f staged next\n", wi, now_ms() - t_begin);
         CK(cudaEventSynchronize(ev_k[b]));
+        memcpy(out_lens + w.first, c->pinned[2 + b], w.count * 4);
+        if (timing) { float kms = 0; cudaEventElapsedTime(&kms, tk0, tk1); fprintf(stderr, "[compress wave %zu] t=%.2f kernel done (kernel %.2f ms)\n", wi, now_ms() - t_begin, kms); cudaEventDestroy(tk0); cudaEventDestroy(tk1); }
         // drain: contiguous host destinations are gathered on the device first, then one D2H
         bool dense = true;
         uint64_t run = 0;
@@ -566,7 +587,6 @@ int sb_compress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, cons
                                    out_lens[w.first + k], cudaMemcpyDeviceToHost, c->s_d2h));
         }
         CK(cudaEventRecord(ev_out[b], c->s_d2h));
-        if (wi >= 1) CK(cudaEventSynchronize(ev_out[b ^ 1]));   // buffer b^1 is reused by wave wi+1's kernel output
     }
     CK(cudaStreamSynchronize(c->s_d2h));
     CK(cudaStreamSynchronize(c->s_compute));
@@ -623,10 +643,16 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
             pout[b][k] = (uint64_t)(uintptr_t)(c->compact[b].as<uint8_t>() + oat);
             oat += ((uint64_t)out_caps[w.first + k] + 15) & ~(uint64_t)15;
         }
-        CK(cudaMemcpyAsync(c->ptrs_in[b].p, pin[b].data(), w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
-        CK(cudaMemcpyAsync(c->ptrs_out[b].p, pout[b].data(), w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
-        CK(cudaMemcpyAsync(c->caps[b].p, in_lens + w.first, w.count * 4, cudaMemcpyHostToDevice, c->s_h2d));
-        CK(cudaMemcpyAsync(c->caps[b].as<uint32_t>() + w.count, out_caps + w.first, w.count * 4, cudaMemcpyHostToDevice, c->s_h2d));
+        { int prc = need_pinned(*c, b, w.count * 24 + 64, err); if (prc) return prc; }
+        uint64_t* sp = (uint64_t*)c->pinned[b];
+        memcpy(sp, pin[b].data(), w.count * 8);
+        memcpy(sp + w.count, pout[b].data(), w.count * 8);
+        uint32_t* sl = (uint32_t*)(sp + 2 * w.count);
+        memcpy(sl, in_lens + w.first, w.count * 4);
+        memcpy(sl + w.count, out_caps + w.first, w.count * 4);
+        CK(cudaMemcpyAsync(c->ptrs_in[b].p, sp, w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
+        CK(cudaMemcpyAsync(c->ptrs_out[b].p, sp + w.count, w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
+        CK(cudaMemcpyAsync(c->caps[b].p, sl, w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
         CK(cudaStreamSynchronize(c->s_h2d));
         CK(cudaEventRecord(ev_in[b], c->s_h2d));
         return 0;
@@ -636,6 +662,7 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
         const Wave& w = waves[wi];
         const int b = (int)(wi & 1);
         CK(cudaStreamWaitEvent(c->s_compute, ev_in[b], 0));
+        if (wi >= 2) CK(cudaStreamWaitEvent(c->s_compute, ev_out[b], 0));   // wave wi-2 (same buffers) fully drained
         sb_batch bt;
         memset(&bt, 0, sizeof bt);
         bt.in_ptrs = (const uint8_t* const*)c->ptrs_in[b].p; bt.in_lens = c->caps[b].as<uint32_t>();
@@ -643,12 +670,16 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
         bt.out_lens = c->lens[b].as<uint32_t>(); bt.statuses = c->status[b].as<sb_error>(); bt.count = (uint32_t)w.count;
         rc = launch_k2(*c, bt, c->s_compute, err);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(out_lens + w.first, c->lens[b].p, w.count * 4, cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaMemcpyAsync(statuses + w.first, c->status[b].p, w.count * sizeof(sb_error), cudaMemcpyDeviceToHost, c->s_compute));
+        { int prc = need_pinned(*c, 2 + b, w.count * (4 + sizeof(sb_error)) + 64, err); if (prc) return prc; }
+        sb_error* pst = (sb_error*)c->pinned[2 + b];
+        uint32_t* pln = (uint32_t*)(pst + w.count);
+        CK(cudaMemcpyAsync(pln, c->lens[b].p, w.count * 4, cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaMemcpyAsync(pst, c->status[b].p, w.count * sizeof(sb_error), cudaMemcpyDeviceToHost, c->s_compute));
         CK(cudaEventRecord(ev_k[b], c->s_compute));
-        if (wi >= 1) CK(cudaEventSynchronize(ev_out[b ^ 1]));       // wave wi-1 drained: its buffers may be restaged
-        if (wi + 1 < waves.size()) { rc = stage_in(wi + 1); if (rc) return rc; }   // overlaps the kernel above
+        if (wi + 1 < waves.size()) { rc = stage_in(wi + 1); if (rc) return rc; }   // overlaps the kernel above and the previous drain
         CK(cudaEventSynchronize(ev_k[b]));
+        memcpy(out_lens + w.first, pln, w.count * 4);
+        memcpy(statuses + w.first, pst, w.count * sizeof(sb_error));
         // drain on the third stream; contiguous destinations whose caps are exactly filled go out as one copy
         const uint64_t cbase = (uint64_t)(uintptr_t)c->compact[b].p;
         size_t k = 0;
