@@ -175,6 +175,7 @@ SB_DEVICE bool k1_serial(const uint8_t* win, uint32_t n, uint16_t* table, unsign
             const unsigned fi = vm == 0xFFFFFFFFu ? 32 : ffs(~vm) - 1;
             const unsigned fh = hm ? ffs(hm) - 1 : 32;
             const unsigned ncommit = fh < fi ? fh + 1 : fi;    // lanes [0, ncommit) perform their insert
+            syncwarp();                                         // probe reads precede the batch's inserts
             if (lane < ncommit) {
                 const uint32_t later = same & ~((2u << lane) - 1u) & (ncommit >= 32 ? 0xFFFFFFFFu : ((1u << ncommit) - 1u));
                 if (!later) table[h] = (uint16_t)pos;           // last writer of a slot wins
@@ -323,7 +324,8 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
 #ifdef SB_EMU_TRACE
     if (lane == 0) fprintf(stderr, "win w=%u i0=%u rm=%d skip=%u E=%08x f=%u CS=%08x C=%08x\n", w, i0, (int)st.rematch, st.skip, E, f, CS, C);
 #endif
-    if (ins) table[h] = (uint16_t)p;
+    syncwarp();                                                  // every lane's probe read precedes the commit
+    if (ins) table[h] = (uint16_t)p;                             // same-slot stores: exactly one lands (detected below)
     syncwarp();
     const bool clash = ins && table[h] != (uint16_t)p;
     uint32_t cut = 32;                                           // window accepted up to (not including) this lane
