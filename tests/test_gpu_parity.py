@@ -368,3 +368,64 @@ def test_config3_urls_tiled_decompress(snap, oracle):
         want = torch.frombuffer(bytearray(blk), dtype=torch.uint8).to(dev)
         assert bool((view[:, k, :len(blk)] == want).all())
         assert bool((dlen.view(reps, 11)[:, k] == len(blk)).all())
+
+
+def test_unaligned_units_device_api(snap, oracle):
+    """Unit pointers at odd byte offsets (pointer-array addressing): K1 reads the window in place
+    from global memory with aligned word loads around an unaligned base; K2 likewise."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import gpu_helpers
+    L = gpu_helpers.lib()
+    dev = torch.device("cuda:0")
+    data = corpus("alice29.txt") + corpus("geo.protodata")
+    rng = random.Random(17)
+    units, offs, at = [], [], 1
+    for _ in range(96):
+        n = rng.choice([1, 15, 16, 17, 31, 100, 4097, 20000, 65535, 65536])
+        o = rng.randrange(0, len(data) - n)
+        units.append(data[o:o + n]); offs.append(at); at += n + rng.choice([0, 1, 2, 3, 5])
+    blob = bytearray(at + 64)
+    for u, o in zip(units, offs):
+        blob[o:o + len(u)] = u
+    t_in = torch.frombuffer(blob, dtype=torch.uint8).to(dev)
+    stride = 76544 + 3                                           # odd output stride: unaligned destinations too
+    t_c = torch.zeros(len(units) * stride + 64, dtype=torch.uint8, device=dev)
+    in_ptrs = torch.tensor([t_in.data_ptr() + o for o in offs], dtype=torch.int64, device=dev)
+    in_lens = torch.tensor([len(u) for u in units], dtype=torch.int32, device=dev)
+    c_lens = torch.zeros(len(units), dtype=torch.int32, device=dev)
+    b = snap._lib.SbBatch()
+    b.in_ptrs, b.in_lens = in_ptrs.data_ptr(), in_lens.data_ptr()
+    b.out_base, b.out_stride, b.out_cap_uniform, b.out_lens, b.count = t_c.data_ptr() + 1, stride, stride, c_lens.data_ptr(), len(units)
+    e = snap._lib.SbError()
+    st = torch.cuda.current_stream().cuda_stream
+    assert L.sb_compress_batch_device(C.byref(b), st, C.byref(e)) == 0
+    torch.cuda.synchronize()
+    host_c, cl = t_c.cpu().numpy(), c_lens.cpu().numpy()
+    for i, u in enumerate(units):
+        assert bytes(host_c[1 + i * stride:1 + i * stride + int(cl[i])]) == oracle.compress(u), i
+    # decode from the unaligned compressed streams into unaligned outputs
+    ostride = 65536 + 5
+    t_o = torch.zeros(len(units) * ostride + 64, dtype=torch.uint8, device=dev)
+    d_lens = torch.zeros(len(units), dtype=torch.int32, device=dev)
+    stt = torch.zeros(len(units) * 4, dtype=torch.int64, device=dev)
+    b2 = snap._lib.SbBatch()
+    b2.in_base, b2.in_stride, b2.in_lens = t_c.data_ptr() + 1, stride, c_lens.data_ptr()
+    b2.out_base, b2.out_stride, b2.out_cap_uniform = t_o.data_ptr() + 3, ostride, 65536
+    b2.out_lens, b2.statuses, b2.count = d_lens.data_ptr(), stt.data_ptr(), len(units)
+    assert L.sb_decompress_batch_device(C.byref(b2), st, C.byref(e)) == 0
+    torch.cuda.synchronize()
+    assert int(stt.view(len(units), 4)[:, 0].abs().sum()) == 0
+    host_o = t_o.cpu().numpy()
+    for i, u in enumerate(units):
+        assert bytes(host_o[3 + i * ostride:3 + i * ostride + len(u)]) == u, i
+
+
+def test_large_multiblock_raw_stream(snap, oracle):
+    """One raw stream of 24 MB (367 blocks behind a single varint): blocks are compressed in parallel
+    and gathered on the device; the raw decode of it is one serial chain (the format has no block markers)."""
+    data = (corpus("lcet10.txt") + corpus("kppkn.gtb") + corpus("html_x_4")) * 24
+    c = snap.raw.Encoder().compress_vec(data)
+    assert c == oracle.compress(data)
+    assert snap.raw.Decoder().decompress_vec(c) == data
