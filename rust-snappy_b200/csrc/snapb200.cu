@@ -465,9 +465,11 @@ std::vector<Wave> plan_waves(const uint32_t* in_lens, size_t count, const uint32
     while (i < count) {
         Wave cur{i, 0, 0};
         uint64_t outb = 0;
+        // ramp-up: the first waves are small so the first kernel starts after ~1 ms of H2D, not ~10
+        const size_t limit = w.size() == 0 ? WAVE_BYTES / 8 : w.size() == 1 ? WAVE_BYTES / 2 : WAVE_BYTES;
         while (i < count && cur.count < (1u << 20)) {
             uint64_t add = in_lens[i], oadd = out_caps ? out_caps[i] : 0;
-            if (cur.count && (cur.in_bytes + add > WAVE_BYTES || outb + oadd > 2 * WAVE_BYTES)) break;
+            if (cur.count && (cur.in_bytes + add > limit || outb + oadd > 2 * limit)) break;
             cur.in_bytes += add + 16; outb += oadd; cur.count++; i++;
         }
         w.push_back(cur);
