@@ -163,6 +163,8 @@ def run_ours(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        # keep stdout for the one JSON line: NCCL's banner/debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     snap = graft.load_package()
     L = snap._lib.lib()
