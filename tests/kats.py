@@ -91,3 +91,27 @@ def small_regular_inputs():
         out.append(bytes((j % 10) + ord("a") for j in range(i)))
         i += 23
     return out
+
+
+def adversarial_blocks(seed=2024):
+    """Synthetic blocks aimed at the rare paths of the parsers: zero runs (one giant overlapping copy, copy
+    splitting at 64/60), incompressible data (scan stride growth), tiny alphabets (dense slot clashes inside a
+    32-position window), periodic data around the copy-1/copy-2 offset and length limits, sizes around the
+    table-size and window boundaries."""
+    import random
+    rng = random.Random(seed)
+
+    def rnd(n, a=256):
+        return bytes(rng.randrange(a) for _ in range(n))
+
+    units = [bytes(65536), rnd(65536), rnd(65536, 4)]
+    for per in (1, 2, 3, 5, 7, 12, 31, 32, 33, 63, 64, 65, 67, 68, 69, 127, 128, 129, 2047, 2048, 2049, 4095, 4099):
+        pat = rnd(per)
+        units.append((pat * (65536 // per + 1))[:65536])
+    units.append(rnd(30000) + bytes(5536) + rnd(30000))
+    units.append((rnd(200) + bytes(100)) * 218 + rnd(136))
+    blk = rnd(1000)
+    units.append(b"".join(blk[:rng.randrange(4, 80)] + rnd(rng.randrange(0, 20)) for _ in range(1500))[:65536])
+    for n in (17, 18, 31, 32, 33, 47, 48, 63, 64, 65, 100, 255, 256, 257, 1023, 1025, 8191, 8192, 8193, 16384, 32768, 65535):
+        units.append(rnd(n, 8))
+    return units

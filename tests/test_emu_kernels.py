@@ -8,7 +8,8 @@ import pytest
 
 import emu_helpers as emu
 from conftest import corpus
-from kats import COPY_CLOSE_TO_END, DECODE_ERRORS, RANDOM, small_copy_inputs, small_regular_inputs
+from kats import (COPY_CLOSE_TO_END, DECODE_ERRORS, RANDOM, adversarial_blocks, small_copy_inputs,
+                  small_regular_inputs)
 
 
 def blocks_of(data):
@@ -73,3 +74,23 @@ def test_k2_fuzz_against_oracle(oracle):
             want = (e.err, b"")
         assert (st, out if st[0] == "Ok" else b"") == want
         assert guard == b"\xee" * 16
+
+
+@pytest.mark.parametrize("mode", ["multi", "gw", "sm"])
+def test_k1_adversarial_blocks_all_layouts(oracle, mode):
+    """Every K1 layout (7 pairs per CTA / global window / shared-memory window) on the rare-path blocks."""
+    units = adversarial_blocks()
+    got = emu.compress_units(units, multi=(mode == "multi"), global_window=(mode == "gw"), parsers=1, grid=2)
+    assert [i for i, (c, u) in enumerate(zip(got, units)) if c != oracle.compress(u)] == []
+
+
+def test_k1_pipelined_parsers(oracle):
+    """The NP=2 token-passing variant (kept behind SNAPB200_K1_NP) stays bit-exact."""
+    units = adversarial_blocks()[:12] + [corpus("alice29.txt")[:65536], corpus("html")[:65536]]
+    assert emu.compress_units(units, parsers=2) == [oracle.compress(u) for u in units]
+
+
+def test_k2_adversarial_blocks(oracle):
+    units = adversarial_blocks()
+    res = emu.decompress_units([oracle.compress(u) for u in units], [len(u) for u in units], grid=2, block=128)
+    assert [i for i, (r, u) in enumerate(zip(res, units)) if r[0][0] != "Ok" or r[1] != u or r[2] != b"\xee" * 16] == []

@@ -10,7 +10,8 @@ import random
 import pytest
 
 from conftest import CORPUS, corpus
-from kats import (COPY_CLOSE_TO_END, DECODE_ERRORS, RANDOM, small_copy_inputs, small_regular_inputs)
+from kats import (COPY_CLOSE_TO_END, DECODE_ERRORS, RANDOM, adversarial_blocks, small_copy_inputs,
+                  small_regular_inputs)
 
 pytestmark = pytest.mark.gpu
 
@@ -429,3 +430,13 @@ def test_large_multiblock_raw_stream(snap, oracle):
     c = snap.raw.Encoder().compress_vec(data)
     assert c == oracle.compress(data)
     assert snap.raw.Decoder().decompress_vec(c) == data
+
+
+def test_adversarial_blocks(snap, oracle):
+    """Rare parser paths (zero runs, incompressible data, dense slot clashes, offset/length limits)."""
+    import gpu_helpers
+    units = adversarial_blocks()
+    got = gpu_helpers.compress_batch_host(units)
+    assert [i for i, (g, u) in enumerate(zip(got, units)) if g != oracle.compress(u)] == []
+    back = gpu_helpers.decompress_batch_host(got, [len(u) for u in units])
+    assert [i for i, (u, (st, b)) in enumerate(zip(units, back)) if st[0] != "Ok" or b != u] == []
