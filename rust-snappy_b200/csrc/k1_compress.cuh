@@ -235,9 +235,11 @@ SB_DEVICE uint32_t k1_double(uint32_t E, bool eq, uint32_t L) {
         if ((E >> e) & 1u) T = e;
         else { const uint32_t m = e + 1 < 32 ? E >> (e + 1) : 0u; T = m ? e + 1 + (uint32_t)(ffs(m) - 1) : 64; }
     }
+    // copies are >= 4 bytes long and do not overlap, so a 32-position window holds at most 8 copy
+    // starts on any chain: three doubling rounds (2^3 nodes) always reach the end of the chain
     uint32_t M = 1u << lane;
 #pragma unroll
-    for (int r = 0; r < 5; r++) {
+    for (int r = 0; r < 3; r++) {
         const uint32_t M2 = shfl(M, T & 31u), T2 = shfl(T, T & 31u);
         if (T < 32) { M |= M2; T = T2; }
     }

@@ -99,9 +99,11 @@ SB_DEVICE uint32_t k2_decode_stream(const uint8_t* in, uint32_t n, uint8_t* dst,
         uint32_t E = !valid ? 64u : spill ? 64u : (uint32_t)(lane + hdr + (kind == 0 ? (uint32_t)len : 0u));
 
         // ---- true element starts: pointer doubling from every lane, read lane 0
+        // every element occupies at least 2 compressed bytes (tag + payload/offset byte), so the chain
+        // from lane 0 has at most 16 nodes inside the window: four doubling rounds always suffice
         uint32_t M = 1u << lane;
 #pragma unroll
-        for (int r = 0; r < 5; r++) {
+        for (int r = 0; r < 4; r++) {
             const uint32_t M2 = shfl(M, E & 31u), E2 = shfl(E, E & 31u);
             if (E < 32) { M |= M2; E = E2; }
         }
