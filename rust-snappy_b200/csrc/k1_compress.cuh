@@ -279,7 +279,7 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
 // from the entry position on. Returns false (state untouched, table restored) when
 // the window must be replayed serially.
 SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
-                         K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre& pre) {
+                         K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre& pre, const K1Seq* nxt = nullptr) {
     const unsigned lane = lane_id();
     const uint32_t w = st.s & ~31u, i0 = st.s - w, p = w + lane;
     const uint32_t h = pre.h, c = pre.c, E = pre.E;
@@ -380,7 +380,21 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         const uint32_t e_last = last + shfl(L, last);
         if (e_last >= 32) {
             st.s = w + e_last; st.rematch = true;
-            if (e_last >= 33) k1_preinsert(win, table, shift, s_limit, st.s);   // e-1 lies beyond this window
+            if (e_last >= 33) {                                   // e-1 lies beyond this window
+                if (nxt && nxt->w == w + 32 && e_last <= 64) {
+                    // ... but inside the next one, whose sequential words are already prefetched: take
+                    // its hash from the lane that holds it instead of paying a global load (:293-295)
+                    if (st.s < s_limit) {
+                        const unsigned nsh = (unsigned)((uintptr_t)(win + nxt->w + lane) & 3u) * 8;
+                        const uint32_t hsel = shfl(K1_HASH(funnel_r(nxt->a0, nxt->a1, nsh)), e_last - 33);
+                        syncwarp();
+                        if (lane == 0) table[hsel] = (uint16_t)(st.s - 1);
+                        syncwarp();
+                    }
+                } else {
+                    k1_preinsert(win, table, shift, s_limit, st.s);
+                }
+            }
         } else {
             st.s = w + 32; st.rematch = false; st.skip = 32 + (31 - e_last);
         }
@@ -465,7 +479,7 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
                     pre = k1_eval(win, table, shift, w, &seq);
                     seq = nxt;
                 }
-                ok = k1_finish(win, n, table, shift, s_limit, st, ring, prod, pre);
+                ok = k1_finish(win, n, table, shift, s_limit, st, ring, prod, pre, NP == 1 ? &seq : nullptr);
             }
             finished = ok ? false : k1_serial(win, n, table, shift, s_limit, st, w + 32, ring, prod);
         }
