@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsnapb200.so")
+SO_PATH = os.environ.get("SNAPB200_LIB") or os.path.join(_HERE, "libsnapb200.so")
 
 
 class SbError(C.Structure):

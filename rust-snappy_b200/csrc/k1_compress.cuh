@@ -30,6 +30,23 @@
 #pragma once
 #include "common.cuh"
 
+#if defined(K1_PROFILE) && defined(__CUDACC__)
+// Optional phase timers for kernel archaeology (tools/k1_phase_profile.sh builds a separate
+// library with -DK1_PROFILE; the product build has none of this).
+__device__ unsigned long long g_k1_prof[16];
+#define K1_TICK(slot) do { const long long _now = clock64(); if (sbk::lane_id() == 0) k1_acc[slot] += (unsigned long long)(_now - k1_t0); k1_t0 = _now; } while (0)
+#define K1_PROF_DECL unsigned long long k1_acc[12] = {0,0,0,0,0,0,0,0,0,0,0,0}; long long k1_t0 = clock64();
+#define K1_PROF_ARGS , unsigned long long* k1_acc, long long& k1_t0
+#define K1_PROF_PASS , k1_acc, k1_t0
+#define K1_PROF_FLUSH do { if (sbk::lane_id() == 0) for (int _i = 0; _i < 12; _i++) atomicAdd(&g_k1_prof[_i], k1_acc[_i]); } while (0)
+#else
+#define K1_TICK(slot) do { } while (0)
+#define K1_PROF_DECL
+#define K1_PROF_ARGS
+#define K1_PROF_PASS
+#define K1_PROF_FLUSH do { } while (0)
+#endif
+
 namespace sbk {
 
 static const uint32_t K1_WIN_BYTES = 65536 + 64;             // window + slack for over-reads
@@ -246,7 +263,7 @@ SB_DEVICE uint32_t k1_double(uint32_t E, bool eq, uint32_t L) {
     return M;
 }
 
-SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w, const K1Seq* seq = nullptr) {
+SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w, const K1Seq* seq K1_PROF_ARGS) {
     const uint32_t p = w + lane_id();
     K1Pre r;
     const uintptr_t aa = (uintptr_t)(win + p);
@@ -271,7 +288,9 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
     }
     r.E = ballot(r.eq);
     r.longs = ballot(r.eq && r.L == 12);
+    K1_TICK(1);                                                  // [1] probe: hash, table, candidate words, compare
     r.M = k1_double(r.E, r.eq, r.L);
+    K1_TICK(2);                                                  // [2] pointer doubling
     return r;
 }
 
@@ -279,7 +298,7 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
 // from the entry position on. Returns false (state untouched, table restored) when
 // the window must be replayed serially.
 SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
-                         K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre& pre, const K1Seq* nxt = nullptr) {
+                         K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre& pre, const K1Seq* nxt K1_PROF_ARGS) {
     const unsigned lane = lane_id();
     const uint32_t w = st.s & ~31u, i0 = st.s - w, p = w + lane;
     const uint32_t h = pre.h, c = pre.c, E = pre.E;
@@ -312,6 +331,7 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         longmask &= ~(1u << j);
         M = k1_double(E, eq, L);
     }
+    K1_TICK(3);                                                  // [3] entry state -> taken copies (+ long extensions)
     // ---- inserted positions = entry..31 minus copy interiors [q+1, e-2]
     const bool taken = (CS >> lane) & 1u;
     uint32_t interior = 0;
@@ -326,6 +346,7 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
 #ifdef SB_EMU_TRACE
     if (lane == 0) fprintf(stderr, "win w=%u i0=%u rm=%d skip=%u E=%08x f=%u CS=%08x C=%08x\n", w, i0, (int)st.rematch, st.skip, E, f, CS, C);
 #endif
+    K1_TICK(4);                                                  // [4] interiors / inserted mask
     syncwarp();                                                  // every lane's probe read precedes the commit
     if (ins) table[h] = (uint16_t)p;                             // same-slot stores: exactly one lands (detected below)
     syncwarp();
@@ -369,6 +390,7 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
             return true;
         }
     }
+    K1_TICK(5);                                                  // [5] commit + verify (+ clash handling)
     // ---- publish the copies and leave the window
     const uint32_t ncopy = popc(CS);
     if (ncopy) {
@@ -376,6 +398,7 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         if (taken) ring.ev[(head.head + popc(CS & ((1u << lane) - 1u))) & (ring.size - 1)] = k1_event(p, L, p - c);
         head.head += ncopy;
         if (head.head - head.published >= K1_PUBLISH) k1_publish(ring, head);
+        K1_TICK(6);                                              // [6] event ring
         const unsigned last = 31 - clz(CS);
         const uint32_t e_last = last + shfl(L, last);
         if (e_last >= 32) {
@@ -402,13 +425,15 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         st.skip = st.rematch ? 32 + (31 - i0) : st.skip + (32 - i0);
         st.s = w + 32; st.rematch = false;
     }
+    K1_TICK(7);                                                  // [7] exit state / copy-end insert
     return true;
 }
 
 SB_DEVICE bool k1_window(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
                          K1State& st, const K1Ring& ring, K1Prod& head) {
-    const K1Pre pre = k1_eval(win, table, shift, st.s & ~31u);
-    return k1_finish(win, n, table, shift, s_limit, st, ring, head, pre);
+    K1_PROF_DECL
+    const K1Pre pre = k1_eval(win, table, shift, st.s & ~31u, nullptr K1_PROF_PASS);
+    return k1_finish(win, n, table, shift, s_limit, st, ring, head, pre, nullptr K1_PROF_PASS);
 }
 
 // Parser warps: block visible through `win`, n >= 17. NP warps take turns over the
@@ -435,6 +460,7 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
     const unsigned bar_mine = 1 + k, bar_next = 1 + (k + 1) % NP;
     K1Seq seq;
     seq.a0 = seq.a1 = seq.a2 = seq.a3 = 0; seq.w = 0xFFFFFFFFu;
+    K1_PROF_DECL
     uint32_t my = k;
     K1State lst;                                                   // NP == 1: parse state kept in registers
     lst.s = 1; lst.skip = 32; lst.rematch = false;
@@ -445,7 +471,7 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
         K1Pre pre;
         pre.h = pre.c = pre.L = pre.E = pre.M = pre.longs = 0; pre.eq = false;
         uint32_t w = my * 32;
-        if (NP > 1 && !first && w + 32 < s_limit) { pre = k1_eval(win, table, shift, w); have = true; }
+        if (NP > 1 && !first && w + 32 < s_limit) { pre = k1_eval(win, table, shift, w, nullptr K1_PROF_PASS); have = true; }
         if (NP > 1 && !first) bar_sync(bar_mine, 64);              // token arrives
         first = false;
         K1State st;
@@ -476,12 +502,14 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
                 if (!have) {
                     K1Seq nxt = seq;
                     if (NP == 1 && w + 96 < n) nxt = k1_fetch_seq(win, w + 32);   // issue next window's loads now
-                    pre = k1_eval(win, table, shift, w, &seq);
+                    K1_TICK(0);                                      // [0] loop top / state checks / prefetch issue
+                    pre = k1_eval(win, table, shift, w, &seq K1_PROF_PASS);
                     seq = nxt;
                 }
-                ok = k1_finish(win, n, table, shift, s_limit, st, ring, prod, pre, NP == 1 ? &seq : nullptr);
+                ok = k1_finish(win, n, table, shift, s_limit, st, ring, prod, pre, NP == 1 ? &seq : nullptr K1_PROF_PASS);
             }
-            finished = ok ? false : k1_serial(win, n, table, shift, s_limit, st, w + 32, ring, prod);
+            if (!ok) { K1_TICK(8); finished = k1_serial(win, n, table, shift, s_limit, st, w + 32, ring, prod); K1_TICK(9); }   // [9] serial path
+            else finished = false;
         }
         if (finished) {
             k1_push(ring, prod, k1_event(n, 0, 0));                // end marker -> trailing literal (:417-426)
@@ -490,6 +518,8 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
         if (NP == 1) {
             lst = st;
             if (finished) {
+                K1_TICK(10);
+                K1_PROF_FLUSH;
                 syncwarp();
                 if (lane == 0) { ctrl[6] = prod.head; ctrl[7] = prod.published; }
                 return;
