@@ -89,7 +89,7 @@ struct K1Prod {
     uint32_t published;   // value of ctrl[0]
     uint32_t tail_seen;   // last value read from ctrl[1]
 };
-static const uint32_t K1_PUBLISH = 24;
+static const uint32_t K1_PUBLISH = 64;   // a publish costs a CTA fence behind global stores (~0.5k cycles): amortise it
 
 SB_DEVICE void k1_publish(const K1Ring& r, K1Prod& pr) {
     if (pr.published == pr.head) return;
@@ -226,20 +226,20 @@ SB_DEVICE bool k1_serial(const uint8_t* win, uint32_t n, uint16_t* table, unsign
 struct K1Pre {
     uint32_t h;      // hash of this lane's position
     uint32_t c;      // candidate read from the table
-    uint32_t L;      // match length: exact up to 11, 12 = "12 or more"
+    uint32_t L;      // match length: exact up to 15, 16 = "16 or more"
     uint32_t E;      // ballot: a probe at lane i would hit
     uint32_t M;      // copy starts reachable from this lane (pointer doubling), valid if !(M & longs)
-    uint32_t longs;  // ballot: hit whose length is only known to be >= 12
+    uint32_t longs;  // ballot: hit whose length is only known to be >= 16
     bool eq;
 };
 // the four sequential words a lane needs for a window, fetched one window ahead when the
 // window lives in global memory (hides one L2 round trip per window)
-struct K1Seq { uint32_t a0, a1, a2, a3, w; };
+struct K1Seq { uint32_t a0, a1, a2, a3, a4, w; };
 SB_DEVICE K1Seq k1_fetch_seq(const uint8_t* win, uint32_t w) {
     const uintptr_t aa = (uintptr_t)(win + w + lane_id());
     const uint32_t* aw = (const uint32_t*)(aa & ~(uintptr_t)3);
     K1Seq q;
-    q.a0 = aw[0]; q.a1 = aw[1]; q.a2 = aw[2]; q.a3 = aw[3]; q.w = w;
+    q.a0 = aw[0]; q.a1 = aw[1]; q.a2 = aw[2]; q.a3 = aw[3]; q.a4 = aw[4]; q.w = w;
     return q;
 }
 
@@ -268,26 +268,30 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
     K1Pre r;
     const uintptr_t aa = (uintptr_t)(win + p);
     const unsigned ash = (unsigned)(aa & 3u) * 8;
-    uint32_t a0, a1, a2, a3;
-    if (seq && seq->w == w) { a0 = seq->a0; a1 = seq->a1; a2 = seq->a2; a3 = seq->a3; }
-    else { const K1Seq q = k1_fetch_seq(win, w); a0 = q.a0; a1 = q.a1; a2 = q.a2; a3 = q.a3; }
+    uint32_t a0, a1, a2, a3, a4;
+    if (seq && seq->w == w) { a0 = seq->a0; a1 = seq->a1; a2 = seq->a2; a3 = seq->a3; a4 = seq->a4; }
+    else { const K1Seq q = k1_fetch_seq(win, w); a0 = q.a0; a1 = q.a1; a2 = q.a2; a3 = q.a3; a4 = q.a4; }
     const uint32_t cur = funnel_r(a0, a1, ash);
     r.h = K1_HASH(cur);
     r.c = table[r.h];
     const uintptr_t ba = (uintptr_t)(win + r.c);
     const uint32_t* bw = (const uint32_t*)(ba & ~(uintptr_t)3);
     const unsigned bsh = (unsigned)(ba & 3u) * 8;
-    const uint32_t b0 = bw[0], b1 = bw[1], b2 = bw[2], b3 = bw[3];
+    const uint32_t b0 = bw[0], b1 = bw[1], b2 = bw[2], b3 = bw[3], b4 = bw[4];
     r.eq = cur == funnel_r(b0, b1, bsh);
     r.L = 4;
     const uint32_t x4 = funnel_r(a1, a2, ash) ^ funnel_r(b1, b2, bsh);
     if (x4) r.L += (uint32_t)(ffs(x4) - 1) >> 3;
     else {
         const uint32_t x8 = funnel_r(a2, a3, ash) ^ funnel_r(b2, b3, bsh);
-        r.L = 8 + (x8 ? (uint32_t)(ffs(x8) - 1) >> 3 : 4);
+        if (x8) r.L = 8 + ((uint32_t)(ffs(x8) - 1) >> 3);
+        else {
+            const uint32_t x12 = funnel_r(a3, a4, ash) ^ funnel_r(b3, b4, bsh);
+            r.L = 12 + (x12 ? (uint32_t)(ffs(x12) - 1) >> 3 : 4);
+        }
     }
     r.E = ballot(r.eq);
-    r.longs = ballot(r.eq && r.L == 12);
+    r.longs = ballot(r.eq && r.L == 16);
     K1_TICK(1);                                                  // [1] probe: hash, table, candidate words, compare
     r.M = k1_double(r.E, r.eq, r.L);
     K1_TICK(2);                                                  // [2] pointer doubling
@@ -326,7 +330,7 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         if (!unk) break;
         const unsigned j = ffs(unk) - 1;
         const uint32_t pj = w + j, cj = shfl(c, j);
-        const uint32_t end = k1_extend(win, n, pj + 12, cj + 12);
+        const uint32_t end = k1_extend(win, n, pj + 16, cj + 16);
         if (lane == j) L = end - pj;
         longmask &= ~(1u << j);
         M = k1_double(E, eq, L);
@@ -471,7 +475,7 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
         K1Pre pre;
         pre.h = pre.c = pre.L = pre.E = pre.M = pre.longs = 0; pre.eq = false;
         uint32_t w = my * 32;
-        if (NP > 1 && !first && w + 32 < s_limit) { pre = k1_eval(win, table, shift, w, nullptr K1_PROF_PASS); have = true; }
+        if (NP > 1 && !first && w + 36 < s_limit) { pre = k1_eval(win, table, shift, w, nullptr K1_PROF_PASS); have = true; }
         if (NP > 1 && !first) bar_sync(bar_mine, 64);              // token arrives
         first = false;
         K1State st;
@@ -494,14 +498,14 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
         if (st.rematch ? st.s >= s_limit : st.s + (st.skip >> 5) > s_limit) finished = true;
         else {
             bool ok = false;
-            if (w + 32 < s_limit && (st.rematch || st.skip < 64)) {
+            if (w + 36 < s_limit && (st.rematch || st.skip < 64)) {
                 if (have) {
                     const uint32_t cn = table[pre.h];
                     if (any(lane >= st.s - w && cn != pre.c)) have = false;   // a slot I depend on moved: probe again
                 }
                 if (!have) {
                     K1Seq nxt = seq;
-                    if (NP == 1 && w + 96 < n) nxt = k1_fetch_seq(win, w + 32);   // issue next window's loads now
+                    if (NP == 1 && w + 100 < n) nxt = k1_fetch_seq(win, w + 32);   // issue next window's loads now
                     K1_TICK(0);                                      // [0] loop top / state checks / prefetch issue
                     pre = k1_eval(win, table, shift, w, &seq K1_PROF_PASS);
                     seq = nxt;
