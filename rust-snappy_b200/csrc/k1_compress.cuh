@@ -263,26 +263,7 @@ SB_DEVICE uint32_t k1_double(uint32_t E, bool eq, uint32_t L) {
     return M;
 }
 
-// Front end of a probe (hash -> table read -> candidate word loads) issued EARLY: right after the
-// previous window's commit, against the table exactly as the next probe will see it, so the L2 round
-// trip of the candidate words overlaps the previous window's bookkeeping instead of stalling the probe.
-struct K1Front {
-    uint32_t h, c, b0, b1, b2, b3, b4, w;
-    bool ok;
-};
-SB_DEVICE K1Front k1_front(const uint8_t* win, const uint16_t* table, unsigned shift, const K1Seq& q) {
-    K1Front f;
-    const unsigned ash = (unsigned)((uintptr_t)(win + q.w + lane_id()) & 3u) * 8;
-    f.h = K1_HASH(funnel_r(q.a0, q.a1, ash));
-    f.c = table[f.h];
-    const uint32_t* bw = (const uint32_t*)((uintptr_t)(win + f.c) & ~(uintptr_t)3);
-    f.b0 = bw[0]; f.b1 = bw[1]; f.b2 = bw[2]; f.b3 = bw[3]; f.b4 = bw[4];
-    f.w = q.w; f.ok = true;
-    return f;
-}
-
-SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w, const K1Seq* seq,
-                        const K1Front* fr K1_PROF_ARGS) {
+SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w, const K1Seq* seq K1_PROF_ARGS) {
     const uint32_t p = w + lane_id();
     K1Pre r;
     const uintptr_t aa = (uintptr_t)(win + p);
@@ -291,17 +272,12 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
     if (seq && seq->w == w) { a0 = seq->a0; a1 = seq->a1; a2 = seq->a2; a3 = seq->a3; a4 = seq->a4; }
     else { const K1Seq q = k1_fetch_seq(win, w); a0 = q.a0; a1 = q.a1; a2 = q.a2; a3 = q.a3; a4 = q.a4; }
     const uint32_t cur = funnel_r(a0, a1, ash);
-    uint32_t b0, b1, b2, b3, b4;
-    if (fr && fr->ok && fr->w == w) {                            // front end already issued after the last commit
-        r.h = fr->h; r.c = fr->c;
-        b0 = fr->b0; b1 = fr->b1; b2 = fr->b2; b3 = fr->b3; b4 = fr->b4;
-    } else {
-        r.h = K1_HASH(cur);
-        r.c = table[r.h];
-        const uint32_t* bw = (const uint32_t*)((uintptr_t)(win + r.c) & ~(uintptr_t)3);
-        b0 = bw[0]; b1 = bw[1]; b2 = bw[2]; b3 = bw[3]; b4 = bw[4];
-    }
-    const unsigned bsh = (unsigned)((uintptr_t)(win + r.c) & 3u) * 8;
+    r.h = K1_HASH(cur);
+    r.c = table[r.h];
+    const uintptr_t ba = (uintptr_t)(win + r.c);
+    const uint32_t* bw = (const uint32_t*)(ba & ~(uintptr_t)3);
+    const unsigned bsh = (unsigned)(ba & 3u) * 8;
+    const uint32_t b0 = bw[0], b1 = bw[1], b2 = bw[2], b3 = bw[3], b4 = bw[4];
     r.eq = cur == funnel_r(b0, b1, bsh);
     r.L = 4;
     const uint32_t x4 = funnel_r(a1, a2, ash) ^ funnel_r(b1, b2, bsh);
@@ -326,7 +302,7 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
 // from the entry position on. Returns false (state untouched, table restored) when
 // the window must be replayed serially.
 SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
-                         K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre& pre, const K1Seq* nxt, K1Front* front K1_PROF_ARGS) {
+                         K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre& pre, const K1Seq* nxt K1_PROF_ARGS) {
     const unsigned lane = lane_id();
     const uint32_t w = st.s & ~31u, i0 = st.s - w, p = w + lane;
     const uint32_t h = pre.h, c = pre.c, E = pre.E;
@@ -419,10 +395,14 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         }
     }
     K1_TICK(5);                                                  // [5] commit + verify (+ clash handling)
-    // ---- leave the window: new parse state first, then the next window's probe front end, and
-    // only then the event ring (table-independent bookkeeping that hides the candidate loads)
+    // ---- publish the copies and leave the window
     const uint32_t ncopy = popc(CS);
     if (ncopy) {
+        k1_wait_space(ring, head, ncopy);
+        if (taken) ring.ev[(head.head + popc(CS & ((1u << lane) - 1u))) & (ring.size - 1)] = k1_event(p, L, p - c);
+        head.head += ncopy;
+        if (head.head - head.published >= K1_PUBLISH) k1_publish(ring, head);
+        K1_TICK(6);                                              // [6] event ring
         const unsigned last = 31 - clz(CS);
         const uint32_t e_last = last + shfl(L, last);
         if (e_last >= 32) {
@@ -450,26 +430,14 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         st.s = w + 32; st.rematch = false;
     }
     K1_TICK(7);                                                  // [7] exit state / copy-end insert
-    if (front) {
-        front->ok = false;
-        if (nxt && nxt->w == w + 32 && (st.s & ~31u) == w + 32 && w + 32 + 36 < s_limit)
-            *front = k1_front(win, table, shift, *nxt);          // table is final for the next probe from here on
-    }
-    if (ncopy) {
-        k1_wait_space(ring, head, ncopy);
-        if (taken) ring.ev[(head.head + popc(CS & ((1u << lane) - 1u))) & (ring.size - 1)] = k1_event(p, L, p - c);
-        head.head += ncopy;
-        if (head.head - head.published >= K1_PUBLISH) k1_publish(ring, head);
-    }
-    K1_TICK(6);                                                  // [6] next front end issue + event ring
     return true;
 }
 
 SB_DEVICE bool k1_window(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
                          K1State& st, const K1Ring& ring, K1Prod& head) {
     K1_PROF_DECL
-    const K1Pre pre = k1_eval(win, table, shift, st.s & ~31u, nullptr, nullptr K1_PROF_PASS);
-    return k1_finish(win, n, table, shift, s_limit, st, ring, head, pre, nullptr, nullptr K1_PROF_PASS);
+    const K1Pre pre = k1_eval(win, table, shift, st.s & ~31u, nullptr K1_PROF_PASS);
+    return k1_finish(win, n, table, shift, s_limit, st, ring, head, pre, nullptr K1_PROF_PASS);
 }
 
 // Parser warps: block visible through `win`, n >= 17. NP warps take turns over the
@@ -496,8 +464,6 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
     const unsigned bar_mine = 1 + k, bar_next = 1 + (k + 1) % NP;
     K1Seq seq;
     seq.a0 = seq.a1 = seq.a2 = seq.a3 = 0; seq.w = 0xFFFFFFFFu;
-    K1Front fr;
-    fr.h = fr.c = fr.b0 = fr.b1 = fr.b2 = fr.b3 = fr.b4 = 0; fr.w = 0xFFFFFFFFu; fr.ok = false;
     K1_PROF_DECL
     uint32_t my = k;
     K1State lst;                                                   // NP == 1: parse state kept in registers
@@ -509,7 +475,7 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
         K1Pre pre;
         pre.h = pre.c = pre.L = pre.E = pre.M = pre.longs = 0; pre.eq = false;
         uint32_t w = my * 32;
-        if (NP > 1 && !first && w + 36 < s_limit) { pre = k1_eval(win, table, shift, w, nullptr, nullptr K1_PROF_PASS); have = true; }
+        if (NP > 1 && !first && w + 36 < s_limit) { pre = k1_eval(win, table, shift, w, nullptr K1_PROF_PASS); have = true; }
         if (NP > 1 && !first) bar_sync(bar_mine, 64);              // token arrives
         first = false;
         K1State st;
@@ -541,11 +507,10 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
                     K1Seq nxt = seq;
                     if (NP == 1 && w + 100 < n) nxt = k1_fetch_seq(win, w + 32);   // issue next window's loads now
                     K1_TICK(0);                                      // [0] loop top / state checks / prefetch issue
-                    pre = k1_eval(win, table, shift, w, &seq, NP == 1 ? &fr : nullptr K1_PROF_PASS);
+                    pre = k1_eval(win, table, shift, w, &seq K1_PROF_PASS);
                     seq = nxt;
                 }
-                fr.ok = false;
-                ok = k1_finish(win, n, table, shift, s_limit, st, ring, prod, pre, NP == 1 ? &seq : nullptr, NP == 1 ? &fr : nullptr K1_PROF_PASS);
+                ok = k1_finish(win, n, table, shift, s_limit, st, ring, prod, pre, NP == 1 ? &seq : nullptr K1_PROF_PASS);
             }
             if (!ok) { K1_TICK(8); finished = k1_serial(win, n, table, shift, s_limit, st, w + 32, ring, prod); K1_TICK(9); }   // [9] serial path
             else finished = false;
