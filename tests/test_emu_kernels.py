@@ -21,14 +21,15 @@ def blocks_of(data):
 def test_k1_k2_corpus_blocks(oracle, name):
     blocks = blocks_of(corpus(name))[:3]
     want = [oracle.compress(b) for b in blocks]
-    assert emu.compress_units(blocks, grid=2) == want
+    assert emu.compress_units(blocks, grid=2, multi=True) == want          # product default: 7 pairs per CTA
+    assert emu.compress_units(blocks[:1], global_window=True) == want[:1]  # one-pair global-window variant
     for (st, out, guard), b in zip(emu.decompress_units(want, [len(b) for b in blocks], grid=2, block=64), blocks):
         assert st[0] == "Ok" and out == b and guard == b"\xee" * 16
 
 
 def test_k1_small_inputs(oracle):
     units = [b"", b"\x00"] + RANDOM + small_copy_inputs() + small_regular_inputs()[::9]
-    assert emu.compress_units(units) == [oracle.compress(u) for u in units]
+    assert emu.compress_units(units, multi=True) == [oracle.compress(u) for u in units]
 
 
 def test_k2_error_kats():
