@@ -455,7 +455,7 @@ int sb_generate_blocks_device(const uint8_t* d_text, uint64_t text_len, uint8_t*
 // Waves of units are staged H2D on one stream, run on a second, and drained D2H
 // on a third, double buffered, so PCIe traffic overlaps the kernels.
 namespace {
-const size_t WAVE_BYTES = (size_t)512 << 20;
+const size_t WAVE_BYTES = (size_t)1 << 30;
 
 struct Wave { size_t first, count; uint64_t in_bytes; };
 
@@ -466,7 +466,7 @@ std::vector<Wave> plan_waves(const uint32_t* in_lens, size_t count, const uint32
         Wave cur{i, 0, 0};
         uint64_t outb = 0;
         // ramp-up: the first waves are small so the first kernel starts after ~1 ms of H2D, not ~10
-        const size_t limit = w.size() == 0 ? WAVE_BYTES / 8 : w.size() == 1 ? WAVE_BYTES / 2 : WAVE_BYTES;
+        const size_t limit = w.size() == 0 ? WAVE_BYTES / 16 : w.size() == 1 ? WAVE_BYTES / 4 : WAVE_BYTES;
         while (i < count && cur.count < (1u << 20)) {
             uint64_t add = in_lens[i], oadd = out_caps ? out_caps[i] : 0;
             if (cur.count && (cur.in_bytes + add > limit || outb + oadd > 2 * limit)) break;

@@ -7,7 +7,7 @@ import __graft_entry__ as graft
 from bench import load_text, BLOCK, MUL
 snap = graft.load_package(); L = snap._lib.lib(); err = snap._lib.SbError()
 torch.cuda.set_device(0); dev = torch.device("cuda:0")
-n = 65536
+n = 131072
 text = load_text()
 t_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).to(dev)
 t_in = torch.empty(n * BLOCK, dtype=torch.uint8, device=dev)
