@@ -440,3 +440,44 @@ def test_adversarial_blocks(snap, oracle):
     assert [i for i, (g, u) in enumerate(zip(got, units)) if g != oracle.compress(u)] == []
     back = gpu_helpers.decompress_batch_host(got, [len(u) for u in units])
     assert [i for i, (u, (st, b)) in enumerate(zip(units, back)) if st[0] != "Ok" or b != u] == []
+
+
+class _Dribble(io.RawIOBase):
+    """A reader that returns at most k bytes per read() call (short reads are legal for io::Read)."""
+
+    def __init__(self, data, k):
+        self._d, self._at, self._k = data, 0, k
+
+    def readable(self):
+        return True
+
+    def read(self, n=-1):
+        n = self._k if n is None or n < 0 else min(n, self._k)
+        out = self._d[self._at:self._at + n]
+        self._at += len(out)
+        return out
+
+
+def test_property_frame_roundtrip_stream(snap, oracle):
+    """qc_roundtrip_stream (test/tests.rs:522-534) plus random write sizes and short reads:
+    write::FrameEncoder output is modelled chunk by chunk with the oracle, read::FrameDecoder
+    gives the bytes back even from a reader that dribbles 1..7 bytes per call."""
+    rng = random.Random(4242)
+    for case in range(40):
+        n = rng.randrange(1, 10000) if case % 4 else rng.randrange(60000, 200000)
+        alpha = rng.choice([2, 7, 256])
+        data = bytes(rng.randrange(alpha) for _ in range(n))
+        w = snap.write.FrameEncoder(io.BytesIO())
+        at = 0
+        while at < n:
+            k = rng.choice([1, 5, 100, 4096, 65535, 65536, 65537, 100000])
+            w.write(data[at:at + k]); at += k
+        framed = w.into_inner().getvalue()
+        assert framed[:10] == b"\xff\x06\x00\x00sNaPpY"
+        assert oracle.frame_decode(framed) == data                 # any legal chunking decodes with the oracle
+        assert snap.frame.decode_all(framed) == data
+        if n < 20000:
+            assert snap.read.FrameDecoder(_Dribble(framed, rng.randrange(1, 8))).read_to_end() == data
+        # single write_all == oracle's single-stream bytes
+        w2 = snap.write.FrameEncoder(io.BytesIO()); w2.write_all(data)
+        assert w2.into_inner().getvalue() == oracle.frame_encode(data)
