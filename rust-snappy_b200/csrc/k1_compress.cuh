@@ -475,7 +475,14 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
         K1Pre pre;
         pre.h = pre.c = pre.L = pre.E = pre.M = pre.longs = 0; pre.eq = false;
         uint32_t w = my * 32;
-        if (NP > 1 && !first && w + 36 < s_limit) { pre = k1_eval(win, table, shift, w, nullptr K1_PROF_PASS); have = true; }
+        if (NP > 1 && !first && w + 36 < s_limit) {
+            // my window after this one: start its sequential-word loads now, they are back by the time I probe it
+            K1Seq nx = seq;
+            if (w + NP * 32 + 100 < n) nx = k1_fetch_seq(win, w + NP * 32);
+            pre = k1_eval(win, table, shift, w, &seq K1_PROF_PASS);
+            seq = nx;
+            have = true;
+        }
         if (NP > 1 && !first) bar_sync(bar_mine, 64);              // token arrives
         first = false;
         K1State st;
