@@ -247,11 +247,10 @@ SB_DEVICE K1Seq k1_fetch_seq(const uint8_t* win, uint32_t w) {
 SB_DEVICE uint32_t k1_double(uint32_t E, bool eq, uint32_t L) {
     const unsigned lane = lane_id();
     const uint32_t e = lane + L;
+    // next copy start after a copy ending at e: a rematch hit at e itself, else the first later hit
+    // of the scan -- i.e. simply the first hit at or after e
     uint32_t T = 64;
-    if (eq && e < 32) {
-        if ((E >> e) & 1u) T = e;
-        else { const uint32_t m = e + 1 < 32 ? E >> (e + 1) : 0u; T = m ? e + 1 + (uint32_t)(ffs(m) - 1) : 64; }
-    }
+    if (eq && e < 32) { const uint32_t m = E >> e; if (m) T = e + (uint32_t)(ffs(m) - 1); }
     // copies are >= 4 bytes long and do not overlap, so a 32-position window holds at most 8 copy
     // starts on any chain: three doubling rounds (2^3 nodes) always reach the end of the chain
     uint32_t M = 1u << lane;
@@ -314,10 +313,8 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
         const uint32_t m = E >> x;
         return m ? x + (uint32_t)(ffs(m) - 1) : 32;
     };
-    uint32_t f;
-    if (st.rematch) f = ((E >> i0) & 1u) ? i0 : nextbit(i0 + 1);
-    else {
-        f = nextbit(i0);
+    const uint32_t f = nextbit(i0);                              // rematch probe at i0 or scan from i0: first hit at/after i0
+    if (!st.rematch) {
         const uint32_t probes = f < 32 ? f - i0 + 1 : 32 - i0;
         if (st.skip + probes > 64) return false;                 // the run leaves stride 1 inside this window
     }
