@@ -278,16 +278,15 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
     const unsigned bsh = (unsigned)(ba & 3u) * 8;
     const uint32_t b0 = bw[0], b1 = bw[1], b2 = bw[2], b3 = bw[3], b4 = bw[4];
     r.eq = cur == funnel_r(b0, b1, bsh);
-    r.L = 4;
-    const uint32_t x4 = funnel_r(a1, a2, ash) ^ funnel_r(b1, b2, bsh);
-    if (x4) r.L += (uint32_t)(ffs(x4) - 1) >> 3;
-    else {
+    // match length, branch-free: bytes 4..15 of both sides, first differing byte wins
+    {
+        const uint32_t x4 = funnel_r(a1, a2, ash) ^ funnel_r(b1, b2, bsh);
         const uint32_t x8 = funnel_r(a2, a3, ash) ^ funnel_r(b2, b3, bsh);
-        if (x8) r.L = 8 + ((uint32_t)(ffs(x8) - 1) >> 3);
-        else {
-            const uint32_t x12 = funnel_r(a3, a4, ash) ^ funnel_r(b3, b4, bsh);
-            r.L = 12 + (x12 ? (uint32_t)(ffs(x12) - 1) >> 3 : 4);
-        }
+        const uint32_t x12 = funnel_r(a3, a4, ash) ^ funnel_r(b3, b4, bsh);
+        const uint32_t l4 = 4 + ((uint32_t)(ffs(x4) - 1) >> 3);       // valid when x4 != 0
+        const uint32_t l8 = 8 + ((uint32_t)(ffs(x8) - 1) >> 3);
+        const uint32_t l12 = x12 ? 12 + ((uint32_t)(ffs(x12) - 1) >> 3) : 16;
+        r.L = x4 ? l4 : x8 ? l8 : l12;
     }
     r.E = ballot(r.eq);
     r.longs = ballot(r.eq && r.L == 16);
@@ -308,12 +307,8 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
     const bool eq = pre.eq;
     uint32_t L = pre.L;
     // first copy start from the entry state
-    auto nextbit = [&](uint32_t x) -> uint32_t {
-        if (x >= 32) return 32;
-        const uint32_t m = E >> x;
-        return m ? x + (uint32_t)(ffs(m) - 1) : 32;
-    };
-    const uint32_t f = nextbit(i0);                              // rematch probe at i0 or scan from i0: first hit at/after i0
+    const uint32_t fm = E >> i0;                                 // i0 < 32
+    const uint32_t f = fm ? i0 + (uint32_t)(ffs(fm) - 1) : 32;   // rematch probe at i0 or scan from i0: first hit at/after i0
     if (!st.rematch) {
         const uint32_t probes = f < 32 ? f - i0 + 1 : 32 - i0;
         if (st.skip + probes > 64) return false;                 // the run leaves stride 1 inside this window
@@ -335,12 +330,10 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
     K1_TICK(3);                                                  // [3] entry state -> taken copies (+ long extensions)
     // ---- inserted positions = entry..31 minus copy interiors [q+1, e-2]
     const bool taken = (CS >> lane) & 1u;
-    uint32_t interior = 0;
-    if (taken && lane < 31) {
-        const uint32_t lo = lane + 1, hi = lane + L - 2;         // L >= 4 -> hi >= lo
-        const uint32_t upto = hi >= 31 ? 0xFFFFFFFFu : ((2u << hi) - 1u);
-        interior = upto & ~((1u << lo) - 1u);
-    }
+    // interior of my copy = lanes [lane+1, lane+L-2] (L >= 4), clipped to the window; branch-free
+    const uint32_t hi_ = lane + L - 2;
+    const uint32_t upto_ = hi_ >= 31 ? 0xFFFFFFFFu : ((2u << hi_) - 1u);
+    const uint32_t interior = taken ? (upto_ & ~((2u << lane) - 1u)) : 0u;   // (2<<31) wraps to 0: lane 31 has no interior
     const uint32_t I = reduce_or(interior);
     const uint32_t C = (0xFFFFFFFFu << i0) & ~I;
     const bool ins = (C >> lane) & 1u;
