@@ -143,11 +143,26 @@ struct K1State {
 #define K1_HASH(x) (((uint32_t)(x) * 0x1E35A7BDu) >> shift)
 
 // after a copy ends at e: `if s >= s_limit return` else insert e-1 (:275-295)
+// table accessors; GT = table in global memory (optionally with an L2 evict-last hint)
+template <bool GT> SB_DEVICE uint32_t k1_tld(const uint16_t* t, uint32_t h) {
+#ifdef K1_TAB_EL
+    if (GT) return ld16_keep(t + h);
+#endif
+    return t[h];
+}
+template <bool GT> SB_DEVICE void k1_tst(uint16_t* t, uint32_t h, uint32_t v) {
+#ifdef K1_TAB_EL
+    if (GT) { st16_keep(t + h, (uint16_t)v); return; }
+#endif
+    t[h] = (uint16_t)v;
+}
+
+template <bool GT = false>
 SB_DEVICE void k1_preinsert(const uint8_t* win, uint16_t* table, unsigned shift, uint32_t s_limit, uint32_t e) {
     if (e < s_limit) {
         const uint32_t h = K1_HASH(k1_rd32(win, e - 1));
         syncwarp();
-        if (lane_id() == 0) table[h] = (uint16_t)(e - 1);
+        if (lane_id() == 0) k1_tst<GT>(table, h, e - 1);
         syncwarp();
     }
 }
@@ -262,6 +277,7 @@ SB_DEVICE uint32_t k1_double(uint32_t E, bool eq, uint32_t L) {
     return M;
 }
 
+template <bool GT = false>
 SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w, const K1Seq* seq K1_PROF_ARGS) {
     const uint32_t p = w + lane_id();
     K1Pre r;
@@ -272,7 +288,7 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
     else { const K1Seq q = k1_fetch_seq(win, w); a0 = q.a0; a1 = q.a1; a2 = q.a2; a3 = q.a3; a4 = q.a4; }
     const uint32_t cur = funnel_r(a0, a1, ash);
     r.h = K1_HASH(cur);
-    r.c = table[r.h];
+    r.c = k1_tld<GT>(table, r.h);
     const uintptr_t ba = (uintptr_t)(win + r.c);
     const uint32_t* bw = (const uint32_t*)(ba & ~(uintptr_t)3);
     const unsigned bsh = (unsigned)(ba & 3u) * 8;
@@ -299,6 +315,9 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
 // Finish one window from a probe result that is known to be current for every lane
 // from the entry position on. Returns false (state untouched, table restored) when
 // the window must be replayed serially.
+// GT: the table lives in global memory (L2) instead of shared memory -- a re-read costs a
+// full L2 round trip there, so slot clashes are found by comparing hashes across lanes.
+template <bool GT>
 SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
                          K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre& pre, const K1Seq* nxt K1_PROF_ARGS) {
     const unsigned lane = lane_id();
@@ -342,16 +361,19 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
 #endif
     K1_TICK(4);                                                  // [4] interiors / inserted mask
     syncwarp();                                                  // every lane's probe read precedes the commit
-    if (ins) table[h] = (uint16_t)p;                             // same-slot stores: exactly one lands (detected below)
+    if (ins) k1_tst<GT>(table, h, p);                            // same-slot stores: exactly one lands (detected below)
     syncwarp();
-    const bool clash = ins && table[h] != (uint16_t)p;
+    uint32_t same = 0;
+    bool clash;
+    if (GT) { same = match_any(ins ? h : 0xFFFF0000u | lane); clash = ins && (same & (same - 1u)) != 0; }
+    else clash = ins && table[h] != (uint16_t)p;
     uint32_t cut = 32;                                           // window accepted up to (not including) this lane
     if (any(clash)) {
         // Two inserted lanes share a slot. A probed lane with a lower inserted lane of the same
         // hash should have seen that lane as its candidate ("victim"): everything before the
         // first victim is still exactly what the serial encoder does, so keep that prefix and
         // restart the window at the victim. Copy-end pre-inserts (e-1) are write-only, never victims.
-        const uint32_t same = match_any(ins ? h : 0xFFFF0000u | lane);
+        if (!GT) same = match_any(ins ? h : 0xFFFF0000u | lane);
         uint32_t pre_bit = 0;
         if (taken && lane + L - 1 < 32) pre_bit = 1u << (lane + L - 1);
         const uint32_t PRE = reduce_or(pre_bit);
@@ -405,11 +427,11 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
                         const unsigned nsh = (unsigned)((uintptr_t)(win + nxt->w + lane) & 3u) * 8;
                         const uint32_t hsel = shfl(K1_HASH(funnel_r(nxt->a0, nxt->a1, nsh)), e_last - 33);
                         syncwarp();
-                        if (lane == 0) table[hsel] = (uint16_t)(st.s - 1);
+                        if (lane == 0) k1_tst<GT>(table, hsel, st.s - 1);
                         syncwarp();
                     }
                 } else {
-                    k1_preinsert(win, table, shift, s_limit, st.s);
+                    k1_preinsert<GT>(win, table, shift, s_limit, st.s);
                 }
             }
         } else {
@@ -427,7 +449,7 @@ SB_DEVICE bool k1_window(const uint8_t* win, uint32_t n, uint16_t* table, unsign
                          K1State& st, const K1Ring& ring, K1Prod& head) {
     K1_PROF_DECL
     const K1Pre pre = k1_eval(win, table, shift, st.s & ~31u, nullptr K1_PROF_PASS);
-    return k1_finish(win, n, table, shift, s_limit, st, ring, head, pre, nullptr K1_PROF_PASS);
+    return k1_finish<false>(win, n, table, shift, s_limit, st, ring, head, pre, nullptr K1_PROF_PASS);
 }
 
 // Parser warps: block visible through `win`, n >= 17. NP warps take turns over the
@@ -441,7 +463,7 @@ SB_DEVICE bool k1_window(const uint8_t* win, uint32_t n, uint16_t* table, unsign
 //   ctrl[3..5] = parse state (s, skip, rematch)   ctrl[6..7] = ring producer (head, published)
 static const uint32_t K1_DONE = 0xFFFFFFFFu;
 
-template <int NP>
+template <int NP, bool GT = false>
 SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* table, const K1Ring& ring,
                                   uint32_t* ctrl, unsigned k) {
     const unsigned lane = lane_id();
@@ -492,10 +514,12 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
             prod.head = ld_volatile(&ctrl[6]); prod.published = ld_volatile(&ctrl[7]);
         }
         bool finished;
-        if (st.rematch ? st.s >= s_limit : st.s + (st.skip >> 5) > s_limit) finished = true;
+        // fast-path test first: when it holds (w + 36 < s_limit, step 1) neither end-of-block test can
+        const bool fast = w + 36 < s_limit && (st.rematch || st.skip < 64);
+        if (!fast && (st.rematch ? st.s >= s_limit : st.s + (st.skip >> 5) > s_limit)) finished = true;
         else {
             bool ok = false;
-            if (w + 36 < s_limit && (st.rematch || st.skip < 64)) {
+            if (fast) {
                 if (have) {
                     const uint32_t cn = table[pre.h];
                     if (any(lane >= st.s - w && cn != pre.c)) have = false;   // a slot I depend on moved: probe again
@@ -504,10 +528,10 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
                     K1Seq nxt = seq;
                     if (NP == 1 && w + 100 < n) nxt = k1_fetch_seq(win, w + 32);   // issue next window's loads now
                     K1_TICK(0);                                      // [0] loop top / state checks / prefetch issue
-                    pre = k1_eval(win, table, shift, w, &seq K1_PROF_PASS);
+                    pre = k1_eval<GT>(win, table, shift, w, &seq K1_PROF_PASS);
                     seq = nxt;
                 }
-                ok = k1_finish(win, n, table, shift, s_limit, st, ring, prod, pre, NP == 1 ? &seq : nullptr K1_PROF_PASS);
+                ok = k1_finish<GT>(win, n, table, shift, s_limit, st, ring, prod, pre, NP == 1 ? &seq : nullptr K1_PROF_PASS);
             }
             if (!ok) { K1_TICK(8); finished = k1_serial(win, n, table, shift, s_limit, st, w + 32, ring, prod); K1_TICK(9); }   // [9] serial path
             else finished = false;
@@ -548,6 +572,13 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
 // Consumes copy events until the end marker (len == 0, pos == n); returns bytes written.
 SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, const K1Ring& ring, uint32_t& tail) {
     const unsigned lane = lane_id();
+#ifdef K1_OUT_EF
+#define K1_OST(p, v) st8_stream((p), (uint8_t)(v))
+#define K1_OCOPY warp_copy_t<true>
+#else
+#define K1_OST(p, v) (*(p) = (uint8_t)(v))
+#define K1_OCOPY warp_copy_t<false>
+#endif
     uint32_t prev_end = 0;
     for (;;) {
         uint32_t avail;
@@ -590,11 +621,11 @@ SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, c
         uint8_t* o = out + d + (incl - size);
         if (lit) {
             const uint32_t mm = lit - 1;
-            if (lhdr == 1) o[0] = (uint8_t)(mm << 2);
-            else if (lhdr == 2) { o[0] = 60 << 2; o[1] = (uint8_t)mm; }
-            else { o[0] = 61 << 2; o[1] = (uint8_t)mm; o[2] = (uint8_t)(mm >> 8); }
+            if (lhdr == 1) K1_OST(o, mm << 2);
+            else if (lhdr == 2) { K1_OST(o, 60 << 2); K1_OST(o + 1, mm); }
+            else { K1_OST(o, 61 << 2); K1_OST(o + 1, mm); K1_OST(o + 2, mm >> 8); }
             o += lhdr;
-            if (lit <= 16) for (uint32_t k = 0; k < lit; k++) o[k] = win[pe + k];
+            if (lit <= 16) for (uint32_t k = 0; k < lit; k++) K1_OST(o + k, win[pe + k]);
         }
         // long literals: whole warp, one at a time
         uint32_t big = ballot(lit > 16);
@@ -603,14 +634,14 @@ SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, c
             big &= big - 1;
             const uint32_t jl = shfl(lit, j), jp = shfl(pe, j);
             const uint32_t jo = shfl((uint32_t)(o - out), j);
-            warp_copy(out + jo, win + jp, jl);
+            K1_OCOPY(out + jo, win + jp, jl);
         }
         if (act && len) {
             o += lit;
-            for (uint32_t k = 0; k < n64; k++) { o[0] = (63 << 2) | 2; o[1] = (uint8_t)off; o[2] = (uint8_t)(off >> 8); o += 3; }
-            if (n60) { o[0] = (59 << 2) | 2; o[1] = (uint8_t)off; o[2] = (uint8_t)(off >> 8); o += 3; }
-            if (fin == 2) { o[0] = (uint8_t)(((off >> 8) << 5) | ((rem - 4) << 2) | 1); o[1] = (uint8_t)off; }
-            else { o[0] = (uint8_t)(((rem - 1) << 2) | 2); o[1] = (uint8_t)off; o[2] = (uint8_t)(off >> 8); }
+            for (uint32_t k = 0; k < n64; k++) { K1_OST(o, (63 << 2) | 2); K1_OST(o + 1, off); K1_OST(o + 2, off >> 8); o += 3; }
+            if (n60) { K1_OST(o, (59 << 2) | 2); K1_OST(o + 1, off); K1_OST(o + 2, off >> 8); o += 3; }
+            if (fin == 2) { K1_OST(o, ((off >> 8) << 5) | ((rem - 4) << 2) | 1); K1_OST(o + 1, off); }
+            else { K1_OST(o, ((rem - 1) << 2) | 2); K1_OST(o + 1, off); K1_OST(o + 2, off >> 8); }
         }
         d += shfl(incl, 31);
         prev_end = shfl(pos + len, m - 1);
@@ -687,50 +718,49 @@ SB_DEVICE void k1_compress_body(const BatchDesc& b, uint32_t flags) {
     }
 }
 
-// One CTA per SM hosting NC independent (parser, emitter) warp pairs: NC hash tables fill the
-// SM's shared memory (7 x 32KB), the window is read in place from global memory and the event
-// rings live in an L2-resident global scratch (`ring_scratch`, K1_RING_GW entries per chain).
-// Pairs synchronise on their own named barrier, so chains never wait for each other.
-template <int NC>
-SB_DEVICE void k1_compress_body_multi(const BatchDesc& b, uint32_t flags, uint64_t* ring_scratch) {
-    uint8_t* sm = smem();
+// One CTA per SM hosting NC + NG independent (parser, emitter) warp pairs. NC hash tables fill
+// the SM's shared memory (7 x 32KB); NG further chains keep their table in an L2-resident global
+// scratch (`gtables`, 32KB per chain): their probe/commit pays L2 latency, so each runs slower
+// than a shared-memory chain, but they only use issue slots and registers the SM had idle.
+// The window is read in place from global memory and the event rings live in an L2-resident
+// global scratch (`ring_scratch`, K1_RING_GW entries per chain). Pairs synchronise on their own
+// named barrier, so chains never wait for each other; because chains differ in speed they take
+// units from a shared counter (`work`, zeroed by the host before the launch) instead of a
+// fixed stride.
+//   ctrl[8] = the unit this pair works on
+template <bool GT>
+SB_DEVICE void k1_chain(const BatchDesc& b, uint32_t flags, uint16_t* table, const K1Ring& ring, uint32_t* ctrl,
+                        uint32_t* work, unsigned bar) {
     const unsigned lane = lane_id(), wid = warp_id();
-    const unsigned c = wid >> 1;                                       // chain within the CTA
     const bool parser = (wid & 1u) == 0;
     const unsigned pt = (wid & 1u) * 32 + lane;                        // thread index within the pair
-    const unsigned bar = 1 + c;
-    uint16_t* table = (uint16_t*)(sm + (size_t)c * K1_TABLE_BYTES);
-    uint32_t* ctrl = (uint32_t*)(sm + (size_t)NC * K1_TABLE_BYTES + c * 64);
-    const uint32_t g = block_idx() * NC + c, nchains = grid_dim() * NC;
-    K1Ring ring;
-    ring.size = K1_RING_GW;
-    ring.ev = ring_scratch + (size_t)g * K1_RING_GW;
-    ring.ctrl = ctrl;
     uint32_t tail = 0;                // emitter's private ring counter (never reset)
     if (pt == 0) { ctrl[0] = 0; ctrl[1] = 0; ctrl[6] = 0; ctrl[7] = 0; }
-    bar_sync(bar, 64);
-    for (uint32_t u = g; u < b.count; u += nchains) {
+    for (;;) {
+        if (pt == 0) ctrl[8] = atomic_add(work, 1u);
+        bar_sync(bar, 64);                                                 // previous unit fully drained, next one chosen
+        const uint32_t u = ld_volatile(&ctrl[8]);
+        if (u >= b.count) return;
         const uint8_t* in = unit_in(b, u);
         const uint32_t n = unit_in_len(b, u);
         uint8_t* out = unit_out(b, u);
         uint32_t d = 0;
         if (flags & 1u) {                                                  // varint header (:120-128)
-            if (n == 0) { if (pt == 0) { out[0] = 0; b.out_lens[u] = 1; } continue; }
             uint32_t v = n;
             while (v >= 0x80) { if (pt == 0) out[d] = (uint8_t)v | 0x80; v >>= 7; d++; }
             if (pt == 0) out[d] = (uint8_t)v;
             d++;
         }
-        if (n == 0) { if (pt == 0) b.out_lens[u] = d; continue; }
-        bar_sync(bar, 64);                                                 // previous unit fully drained
+        if (n == 0) { if (pt == 0) b.out_lens[u] = d; bar_sync(bar, 64); continue; }
         {
             uint32_t tsize = 256;
             while (tsize < 16384 && tsize < n) tsize *= 2;
-            for (uint32_t i = pt; i < tsize / 2; i += 64) ((uint32_t*)table)[i] = 0;   // (:514-516)
+            if (tsize >= 512) for (uint32_t i = pt; i < tsize / 8; i += 64) ((uint4*)table)[i] = make_uint4(0, 0, 0, 0);   // (:514-516)
+            else for (uint32_t i = pt; i < tsize / 2; i += 64) ((uint32_t*)table)[i] = 0;
         }
         bar_sync(bar, 64);
         if (parser) {
-            if (n >= 17) k1_parse_pipelined<1>(in, n, table, ring, ctrl, 0);   // (:140-150)
+            if (n >= 17) k1_parse_pipelined<1, GT>(in, n, table, ring, ctrl, 0);   // (:140-150)
             else {                                                         // tiny block: one literal (:140-146)
                 K1Prod prod;
                 prod.head = ctrl[6]; prod.published = ctrl[7]; prod.tail_seen = 0;
@@ -743,6 +773,20 @@ SB_DEVICE void k1_compress_body_multi(const BatchDesc& b, uint32_t flags, uint64
             if (lane == 0) b.out_lens[u] = d;
         }
     }
+}
+
+template <int NC, int NG>
+SB_DEVICE void k1_compress_body_multi(const BatchDesc& b, uint32_t flags, uint64_t* ring_scratch, uint16_t* gtables,
+                                      uint32_t* work) {
+    uint8_t* sm = smem();
+    const unsigned c = warp_id() >> 1;                                 // chain within the CTA
+    uint32_t* ctrl = (uint32_t*)(sm + (size_t)NC * K1_TABLE_BYTES + c * 64);
+    K1Ring ring;
+    ring.size = K1_RING_GW;
+    ring.ev = ring_scratch + ((size_t)block_idx() * (NC + NG) + c) * K1_RING_GW;
+    ring.ctrl = ctrl;
+    if (NG == 0 || c < NC) k1_chain<false>(b, flags, (uint16_t*)(sm + (size_t)c * K1_TABLE_BYTES), ring, ctrl, work, 1 + c);
+    else k1_chain<true>(b, flags, gtables + ((size_t)block_idx() * NG + (c - NC)) * (K1_TABLE_BYTES / 2), ring, ctrl, work, 1 + c);
 }
 
 }  // namespace sbk

@@ -29,8 +29,15 @@ __global__ void __launch_bounds__(160) k1_s4_kernel(sb_batch b, uint32_t flags) 
 __global__ void __launch_bounds__(64) k1_g1_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<true, 1>(b, flags); }
 __global__ void __launch_bounds__(96) k1_g2_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<true, 2>(b, flags); }
 __global__ void __launch_bounds__(128) k1_g3_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<true, 3>(b, flags); }
-// one CTA per SM, 7 parser/emitter pairs, 7 tables in shared memory, rings in global scratch
-__global__ void __launch_bounds__(448, 1) k1_m7_kernel(sb_batch b, uint32_t flags, uint64_t* rings) { sbk::k1_compress_body_multi<7>(b, flags, rings); }
+// one CTA per SM: 7 parser/emitter pairs with their tables in shared memory + NG pairs with
+// their tables in an L2-resident scratch; rings in global scratch; units taken from `work`
+template <int NG>
+__global__ void __launch_bounds__((7 + NG) * 64, 1)
+k1_m7_kernel(sb_batch b, uint32_t flags, uint64_t* rings, uint16_t* gtables, uint32_t* work) {
+    sbk::k1_compress_body_multi<7, NG>(b, flags, rings, gtables, work);
+}
+const int K1_MAX_NG = 7;
+const size_t K1_M7_SMEM = 7 * sbk::K1_TABLE_BYTES + (7 + K1_MAX_NG) * 64;
 __global__ void __launch_bounds__(128) k2_decompress_kernel(sb_batch b) { sbk::k2_decompress_body(b); }
 __global__ void __launch_bounds__(256) k3_crc_kernel(sb_batch b) { sbk::k3_crc_body(b); }
 __global__ void __launch_bounds__(256) k4_sizes_kernel(sbk::FramePlan p) { sbk::k4_sizes_body(p); }
@@ -44,6 +51,7 @@ const int K1_DEFAULT_NP = 1;
 const int K2_DEFAULT_CTAS_PER_SM = 16;
 const int K1_DEFAULT_GW = 1;
 const int K1_DEFAULT_MULTI = 1;
+const int K1_DEFAULT_NG = 0;
 
 int fail(sb_error* e, uint32_t code, uint64_t a = 0, uint64_t b = 0, uint64_t c = 0) {
     if (e) { e->code = code; e->_pad = 0; e->a = a; e->b = b; e->c = c; }
@@ -82,7 +90,7 @@ struct Ctx {
     int dev = -1, sms = 0;
     bool ready = false;
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-    DevBuf rings;
+    DevBuf rings, gtables, work;   // K1 scratch: event rings, L2-resident tables, unit counter
     DevBuf in[2], slots[2], compact[2], lens[2], csize[2], offs[2], crcs[2], status[2], ptrs_in[2], ptrs_out[2], caps[2];
     void* pinned[4] = {nullptr, nullptr, nullptr, nullptr}; size_t pinned_cap[4] = {0, 0, 0, 0};   // pinned staging: [0,1] descriptors in, [2,3] results out
     std::mutex mu;
@@ -105,8 +113,12 @@ int get_ctx(Ctx** out, sb_error* err) {
         CK(cudaFuncSetAttribute(k1_g1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
         CK(cudaFuncSetAttribute(k1_g2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
         CK(cudaFuncSetAttribute(k1_g3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
-        CK(cudaFuncSetAttribute(k1_m7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(7 * sbk::K1_TABLE_BYTES + 7 * 64)));
-        CK(c.rings.need((size_t)c.sms * 7 * sbk::K1_RING_GW * 8));
+        CK(cudaFuncSetAttribute(k1_m7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
+        CK(cudaFuncSetAttribute(k1_m7_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
+        CK(cudaFuncSetAttribute(k1_m7_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
+        CK(c.rings.need((size_t)c.sms * (7 + K1_MAX_NG) * sbk::K1_RING_GW * 8));
+        CK(c.gtables.need((size_t)c.sms * K1_MAX_NG * sbk::K1_TABLE_BYTES));
+        CK(c.work.need(256));
         CK(cudaStreamCreateWithFlags(&c.s_compute, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking));
@@ -139,9 +151,18 @@ int launch_k1(Ctx& c, const sb_batch& b, uint32_t flags, cudaStream_t st, sb_err
     const size_t sm = gw ? sbk::K1_SMEM_BYTES_GW : sbk::K1_SMEM_BYTES;
     static const int multi = getenv("SNAPB200_K1_MULTI") ? atoi(getenv("SNAPB200_K1_MULTI")) : K1_DEFAULT_MULTI;
     if (multi) {
+        // SNAPB200_K1_NG = extra chains per SM with L2-resident tables (0..7)
+        static const int ng_env = getenv("SNAPB200_K1_NG") ? atoi(getenv("SNAPB200_K1_NG")) : K1_DEFAULT_NG;
+        const unsigned ng = ng_env < 0 ? 0 : ng_env > K1_MAX_NG ? K1_MAX_NG : (unsigned)ng_env;
+        const unsigned chains = 7 + ng;
         unsigned mg = (unsigned)c.sms;
-        if ((uint64_t)mg * 7 > b.count) mg = (unsigned)((b.count + 6) / 7);
-        k1_m7_kernel<<<mg, 448, 7 * sbk::K1_TABLE_BYTES + 7 * 64, st>>>(b, flags, c.rings.as<uint64_t>());
+        if ((uint64_t)mg * chains > b.count) mg = (unsigned)((b.count + chains - 1) / chains);
+        CK(cudaMemsetAsync(c.work.p, 0, 4, st));
+        // the template argument only bounds the chain count (register cap, scratch strides)
+        static const bool wide = getenv("SNAPB200_K1_WIDE") != nullptr;   // experiment: always use the 14-chain build
+        if (ng > 4 || (wide && ng > 0)) k1_m7_kernel<7><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
+        else if (ng > 0) k1_m7_kernel<4><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
+        else k1_m7_kernel<0><<<mg, 7 * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
     } else if (gw) {
         if (np <= 1) k1_g1_kernel<<<grid, 64, sm, st>>>(b, flags);
         else if (np == 2) k1_g2_kernel<<<grid, 96, sm, st>>>(b, flags);

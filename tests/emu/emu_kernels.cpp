@@ -5,10 +5,11 @@
 #include "../../rust-snappy_b200/csrc/k1_compress.cuh"
 #include "../../rust-snappy_b200/csrc/k2_decompress.cuh"
 
-struct K1Args { sb_batch b; uint32_t flags; uint64_t* rings; };
+struct K1Args { sb_batch b; uint32_t flags; uint64_t* rings; uint16_t* gtables; uint32_t* work; };
 static void k1_entry(void* a) {
     K1Args* x = (K1Args*)a;
-    if (x->flags & 0x200u) { sbk::k1_compress_body_multi<7>(x->b, x->flags & 0xFFu, x->rings); return; }
+    if (x->flags & 0x400u) { sbk::k1_compress_body_multi<7, 4>(x->b, x->flags & 0xFFu, x->rings, x->gtables, x->work); return; }   // hybrid: 7 smem + 4 global tables
+    if (x->flags & 0x200u) { sbk::k1_compress_body_multi<7, 0>(x->b, x->flags & 0xFFu, x->rings, x->gtables, x->work); return; }
     const bool gw = x->flags & 0x100u;
     const unsigned np = (x->flags >> 12) & 7u, f = x->flags & 0xFFu;
     if (gw) { if (np <= 1) sbk::k1_compress_body<true, 1>(x->b, f); else if (np == 2) sbk::k1_compress_body<true, 2>(x->b, f); else sbk::k1_compress_body<true, 3>(x->b, f); }
@@ -19,11 +20,16 @@ static void k2_entry(void* a) { sbk::k2_decompress_body(*(sb_batch*)a); }
 extern "C" {
 
 int emu_compress_batch(const sb_batch* b, uint32_t flags, unsigned grid) {
-    K1Args a{*b, flags, nullptr};
-    if (flags & 0x200u) {
-        std::vector<uint64_t> rings((size_t)grid * 7 * sbk::K1_RING_GW, 0xCDCDCDCDCDCDCDCDull);
+    K1Args a{*b, flags, nullptr, nullptr, nullptr};
+    if (flags & 0x600u) {
+        const unsigned ng = (flags & 0x400u) ? 4 : 0;
+        std::vector<uint64_t> rings((size_t)grid * (7 + ng) * sbk::K1_RING_GW, 0xCDCDCDCDCDCDCDCDull);
+        std::vector<uint16_t> gt((size_t)grid * (ng + 1) * (sbk::K1_TABLE_BYTES / 2) + 8, 0xCDCD);
+        uint32_t work = 0;
         a.rings = rings.data();
-        sbemu::launch(grid, 448, 7 * sbk::K1_TABLE_BYTES + 7 * 64, k1_entry, &a);
+        a.gtables = (uint16_t*)(((uintptr_t)gt.data() + 15) & ~(uintptr_t)15);
+        a.work = &work;
+        sbemu::launch(grid, (7 + ng) * 64, 7 * sbk::K1_TABLE_BYTES + (7 + ng) * 64, k1_entry, &a);
         return 0;
     }
     const unsigned np = (flags >> 12) & 7u;

@@ -30,6 +30,7 @@ def test_k1_k2_corpus_blocks(oracle, name):
 def test_k1_small_inputs(oracle):
     units = [b"", b"\x00"] + RANDOM + small_copy_inputs() + small_regular_inputs()[::9]
     assert emu.compress_units(units, multi=True) == [oracle.compress(u) for u in units]
+    assert emu.compress_units(units, hybrid=True) == [oracle.compress(u) for u in units]
 
 
 def test_k2_error_kats():
@@ -77,11 +78,13 @@ def test_k2_fuzz_against_oracle(oracle):
         assert guard == b"\xee" * 16
 
 
-@pytest.mark.parametrize("mode", ["multi", "gw", "sm"])
+@pytest.mark.parametrize("mode", ["multi", "hybrid", "gw", "sm"])
 def test_k1_adversarial_blocks_all_layouts(oracle, mode):
-    """Every K1 layout (7 pairs per CTA / global window / shared-memory window) on the rare-path blocks."""
+    """Every K1 layout (7 pairs per CTA / 7 + 4 pairs with L2-resident tables / global window /
+    shared-memory window) on the rare-path blocks."""
     units = adversarial_blocks()
-    got = emu.compress_units(units, multi=(mode == "multi"), global_window=(mode == "gw"), parsers=1, grid=2)
+    got = emu.compress_units(units, multi=(mode == "multi"), hybrid=(mode == "hybrid"), global_window=(mode == "gw"),
+                             parsers=1, grid=2)
     assert [i for i, (c, u) in enumerate(zip(got, units)) if c != oracle.compress(u)] == []
 
 
