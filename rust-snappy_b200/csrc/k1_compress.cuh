@@ -143,26 +143,11 @@ struct K1State {
 #define K1_HASH(x) (((uint32_t)(x) * 0x1E35A7BDu) >> shift)
 
 // after a copy ends at e: `if s >= s_limit return` else insert e-1 (:275-295)
-// table accessors; GT = table in global memory (optionally with an L2 evict-last hint)
-template <bool GT> SB_DEVICE uint32_t k1_tld(const uint16_t* t, uint32_t h) {
-#ifdef K1_TAB_EL
-    if (GT) return ld16_keep(t + h);
-#endif
-    return t[h];
-}
-template <bool GT> SB_DEVICE void k1_tst(uint16_t* t, uint32_t h, uint32_t v) {
-#ifdef K1_TAB_EL
-    if (GT) { st16_keep(t + h, (uint16_t)v); return; }
-#endif
-    t[h] = (uint16_t)v;
-}
-
-template <bool GT = false>
 SB_DEVICE void k1_preinsert(const uint8_t* win, uint16_t* table, unsigned shift, uint32_t s_limit, uint32_t e) {
     if (e < s_limit) {
         const uint32_t h = K1_HASH(k1_rd32(win, e - 1));
         syncwarp();
-        if (lane_id() == 0) k1_tst<GT>(table, h, e - 1);
+        if (lane_id() == 0) table[h] = (uint16_t)(e - 1);
         syncwarp();
     }
 }
@@ -277,7 +262,6 @@ SB_DEVICE uint32_t k1_double(uint32_t E, bool eq, uint32_t L) {
     return M;
 }
 
-template <bool GT = false>
 SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w, const K1Seq* seq K1_PROF_ARGS) {
     const uint32_t p = w + lane_id();
     K1Pre r;
@@ -288,7 +272,7 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
     else { const K1Seq q = k1_fetch_seq(win, w); a0 = q.a0; a1 = q.a1; a2 = q.a2; a3 = q.a3; a4 = q.a4; }
     const uint32_t cur = funnel_r(a0, a1, ash);
     r.h = K1_HASH(cur);
-    r.c = k1_tld<GT>(table, r.h);
+    r.c = table[r.h];
     const uintptr_t ba = (uintptr_t)(win + r.c);
     const uint32_t* bw = (const uint32_t*)(ba & ~(uintptr_t)3);
     const unsigned bsh = (unsigned)(ba & 3u) * 8;
@@ -361,7 +345,7 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
 #endif
     K1_TICK(4);                                                  // [4] interiors / inserted mask
     syncwarp();                                                  // every lane's probe read precedes the commit
-    if (ins) k1_tst<GT>(table, h, p);                            // same-slot stores: exactly one lands (detected below)
+    if (ins) table[h] = (uint16_t)p;                             // same-slot stores: exactly one lands (detected below)
     syncwarp();
     uint32_t same = 0;
     bool clash;
@@ -427,11 +411,11 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
                         const unsigned nsh = (unsigned)((uintptr_t)(win + nxt->w + lane) & 3u) * 8;
                         const uint32_t hsel = shfl(K1_HASH(funnel_r(nxt->a0, nxt->a1, nsh)), e_last - 33);
                         syncwarp();
-                        if (lane == 0) k1_tst<GT>(table, hsel, st.s - 1);
+                        if (lane == 0) table[hsel] = (uint16_t)(st.s - 1);
                         syncwarp();
                     }
                 } else {
-                    k1_preinsert<GT>(win, table, shift, s_limit, st.s);
+                    k1_preinsert(win, table, shift, s_limit, st.s);
                 }
             }
         } else {
@@ -528,7 +512,7 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
                     K1Seq nxt = seq;
                     if (NP == 1 && w + 100 < n) nxt = k1_fetch_seq(win, w + 32);   // issue next window's loads now
                     K1_TICK(0);                                      // [0] loop top / state checks / prefetch issue
-                    pre = k1_eval<GT>(win, table, shift, w, &seq K1_PROF_PASS);
+                    pre = k1_eval(win, table, shift, w, &seq K1_PROF_PASS);
                     seq = nxt;
                 }
                 ok = k1_finish<GT>(win, n, table, shift, s_limit, st, ring, prod, pre, NP == 1 ? &seq : nullptr K1_PROF_PASS);
@@ -572,13 +556,9 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
 // Consumes copy events until the end marker (len == 0, pos == n); returns bytes written.
 SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, const K1Ring& ring, uint32_t& tail) {
     const unsigned lane = lane_id();
-#ifdef K1_OUT_EF
+    // output is write-once: evict-first stores keep it out of the L2 working set (windows + tables)
 #define K1_OST(p, v) st8_stream((p), (uint8_t)(v))
 #define K1_OCOPY warp_copy_t<true>
-#else
-#define K1_OST(p, v) (*(p) = (uint8_t)(v))
-#define K1_OCOPY warp_copy_t<false>
-#endif
     uint32_t prev_end = 0;
     for (;;) {
         uint32_t avail;

@@ -80,19 +80,6 @@ SB_DEVICE void stcs128(void* p, uint4 v) { __stcs((uint4*)p, v); }
 
 // write-once output bytes: evict-first in L2 so they do not displace data that is re-read
 SB_DEVICE void st8_stream(uint8_t* p, uint8_t v) { __stcs(p, v); }
-// L2 evict-last accessors for small, hot, long-lived global tables
-SB_DEVICE uint32_t ld16_keep(const uint16_t* p) {
-    uint64_t pol; uint16_t v;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("ld.global.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol) : "memory");
-    return v;
-}
-SB_DEVICE void st16_keep(uint16_t* p, uint16_t v) {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(p), "h"(v), "l"(pol) : "memory");
-}
-
 extern __shared__ __align__(128) unsigned char sb_dyn_smem[];
 SB_DEVICE unsigned char* smem() { return sb_dyn_smem; }
 

@@ -51,7 +51,7 @@ const int K1_DEFAULT_NP = 1;
 const int K2_DEFAULT_CTAS_PER_SM = 16;
 const int K1_DEFAULT_GW = 1;
 const int K1_DEFAULT_MULTI = 1;
-const int K1_DEFAULT_NG = 0;
+const int K1_DEFAULT_NG = 5;
 
 int fail(sb_error* e, uint32_t code, uint64_t a = 0, uint64_t b = 0, uint64_t c = 0) {
     if (e) { e->code = code; e->_pad = 0; e->a = a; e->b = b; e->c = c; }
@@ -91,6 +91,8 @@ struct Ctx {
     bool ready = false;
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     DevBuf rings, gtables, work;   // K1 scratch: event rings, L2-resident tables, unit counter
+    cudaEvent_t k1_done = nullptr; // K1 launches share that scratch: each waits for the previous one, whatever its stream
+    std::mutex k1_mu;
     DevBuf in[2], slots[2], compact[2], lens[2], csize[2], offs[2], crcs[2], status[2], ptrs_in[2], ptrs_out[2], caps[2];
     void* pinned[4] = {nullptr, nullptr, nullptr, nullptr}; size_t pinned_cap[4] = {0, 0, 0, 0};   // pinned staging: [0,1] descriptors in, [2,3] results out
     std::mutex mu;
@@ -114,11 +116,12 @@ int get_ctx(Ctx** out, sb_error* err) {
         CK(cudaFuncSetAttribute(k1_g2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
         CK(cudaFuncSetAttribute(k1_g3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
         CK(cudaFuncSetAttribute(k1_m7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
-        CK(cudaFuncSetAttribute(k1_m7_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
+        CK(cudaFuncSetAttribute(k1_m7_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
         CK(cudaFuncSetAttribute(k1_m7_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
         CK(c.rings.need((size_t)c.sms * (7 + K1_MAX_NG) * sbk::K1_RING_GW * 8));
         CK(c.gtables.need((size_t)c.sms * K1_MAX_NG * sbk::K1_TABLE_BYTES));
         CK(c.work.need(256));
+        CK(cudaEventCreateWithFlags(&c.k1_done, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&c.s_compute, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking));
@@ -157,12 +160,16 @@ int launch_k1(Ctx& c, const sb_batch& b, uint32_t flags, cudaStream_t st, sb_err
         const unsigned chains = 7 + ng;
         unsigned mg = (unsigned)c.sms;
         if ((uint64_t)mg * chains > b.count) mg = (unsigned)((b.count + chains - 1) / chains);
+        std::lock_guard<std::mutex> k1lk(c.k1_mu);
+        CK(cudaStreamWaitEvent(st, c.k1_done, 0));
         CK(cudaMemsetAsync(c.work.p, 0, 4, st));
-        // the template argument only bounds the chain count (register cap, scratch strides)
-        static const bool wide = getenv("SNAPB200_K1_WIDE") != nullptr;   // experiment: always use the 14-chain build
-        if (ng > 4 || (wide && ng > 0)) k1_m7_kernel<7><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
-        else if (ng > 0) k1_m7_kernel<4><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
+        // the template argument only bounds the chain count (register cap, scratch strides): up to 12 chains
+        // (24 warps) the parser keeps its 72 registers, 13-14 chains force it down to 64 (measured 6% slower per chain)
+        if (ng > 5) k1_m7_kernel<7><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
+        else if (ng > 0) k1_m7_kernel<5><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
         else k1_m7_kernel<0><<<mg, 7 * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c.k1_done, st));
     } else if (gw) {
         if (np <= 1) k1_g1_kernel<<<grid, 64, sm, st>>>(b, flags);
         else if (np == 2) k1_g2_kernel<<<grid, 96, sm, st>>>(b, flags);

@@ -197,8 +197,6 @@ SB_DEVICE uint4 ldg128(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }
 SB_DEVICE uint8_t ldg8(const void* p) { return *(const uint8_t*)p; }
 SB_DEVICE void stcs128(void* p, uint4 v) { memcpy(p, &v, 16); }
 SB_DEVICE void st8_stream(uint8_t* p, uint8_t v) { *p = v; }
-SB_DEVICE uint32_t ld16_keep(const uint16_t* p) { return *p; }
-SB_DEVICE void st16_keep(uint16_t* p, uint16_t v) { *p = v; }
 
 SB_DEVICE unsigned char* smem() { return sbemu::g_cur->blk->smem; }
 

@@ -442,6 +442,47 @@ def test_adversarial_blocks(snap, oracle):
     assert [i for i, (u, (st, b)) in enumerate(zip(units, back)) if st[0] != "Ok" or b != u] == []
 
 
+_LAYOUT_CHILD = r"""
+import hashlib, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import torch
+torch.cuda.set_device(0)
+import gpu_helpers
+from conftest import corpus
+from kats import adversarial_blocks
+units = adversarial_blocks()
+for name in ("alice29.txt", "html", "urls.10K", "kppkn.gtb", "fireworks.jpeg", "geo.protodata"):
+    d = corpus(name)
+    units += [d[i:i + 65536] for i in range(0, len(d), 65536)]
+units = units * 30                     # > 148 x 14 units so every chain of every SM takes one or more
+got = gpu_helpers.compress_batch_host(units)
+print("DIGEST", len(units), hashlib.sha256(b"".join(len(g).to_bytes(4, "little") + g for g in got)).hexdigest())
+"""
+
+
+@pytest.mark.parametrize("ng", [0, 2, 4, 7])
+def test_k1_chain_layouts(snap, oracle, ng):
+    """K1 with 7 shared-memory-table chains per SM plus `ng` chains whose table lives in L2
+    (SNAPB200_K1_NG is read once per process, hence the child process): same bytes as the oracle."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    units = adversarial_blocks()
+    for name in ("alice29.txt", "html", "urls.10K", "kppkn.gtb", "fireworks.jpeg", "geo.protodata"):
+        d = corpus(name)
+        units += [d[i:i + 65536] for i in range(0, len(d), 65536)]
+    want_one = [oracle.compress(u) for u in units]
+    want = want_one * 30
+    digest = hashlib.sha256(b"".join(len(g).to_bytes(4, "little") + g for g in want)).hexdigest()
+    env = dict(os.environ, SNAPB200_K1_NG=str(ng))
+    res = subprocess.run([sys.executable, "-c", _LAYOUT_CHILD, root], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("DIGEST")][-1].split()
+    assert (int(line[1]), line[2]) == (len(want), digest)
+
+
 class _Dribble(io.RawIOBase):
     """A reader that returns at most k bytes per read() call (short reads are legal for io::Read)."""
 
