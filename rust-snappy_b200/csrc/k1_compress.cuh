@@ -74,8 +74,15 @@ SB_DEVICE uint32_t k1_rd32_end(const uint8_t* win, uint32_t p, uint32_t n) {
 // ---------------------------------------------------------------- event ring
 struct K1Ring {
     uint64_t* ev;        // `size` entries (power of two)
-    uint32_t* ctrl;      // [0]=head (produced), [1]=tail (consumed)
+    uint32_t* ctrl;      // [0]=head (produced), [1]=tail (consumed), [9]=publish count, [10..11]=mbarrier (when `mbar`)
     uint32_t size;
+    // emitter blocks on the mbarrier at ctrl[10] instead of sleep-polling ctrl[0]: experimental, compile with -DK1_MBAR
+    // (tools/build_variant.sh mbar -DK1_MBAR, then SNAPB200_LIB=.../libsnapb200_mbar.so); not measured on hardware yet
+#if defined(K1_MBAR) || defined(SB_EMU)
+    bool mbar = false;
+#else
+    static constexpr bool mbar = false;
+#endif
 };
 SB_DEVICE uint64_t k1_event(uint32_t pos, uint32_t len, uint32_t off) {
     return (uint64_t)pos | ((uint64_t)len << 17) | ((uint64_t)off << 34);
@@ -95,7 +102,13 @@ SB_DEVICE void k1_publish(const K1Ring& r, K1Prod& pr) {
     if (pr.published == pr.head) return;
     threadfence_block();
     syncwarp();
-    if (lane_id() == 0) st_volatile(&r.ctrl[0], pr.head);
+    if (lane_id() == 0) {
+        st_volatile(&r.ctrl[0], pr.head);
+        if (r.mbar) {                                      // head first, then the publish count, then the wake-up
+            st_volatile(&r.ctrl[9], ld_volatile(&r.ctrl[9]) + 1u);
+            mbar_arrive((uint64_t*)&r.ctrl[10]);
+        }
+    }
     pr.published = pr.head;
 }
 SB_DEVICE void k1_wait_space(const K1Ring& r, K1Prod& pr, uint32_t need) {
@@ -563,10 +576,13 @@ SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, c
     for (;;) {
         uint32_t avail;
         for (;;) {
+            // publish count BEFORE the head: if the head read is stale, the phase numbered `pubs` is still open
+            const uint32_t pubs = ring.mbar ? shfl(ld_volatile(&ring.ctrl[9]), 0) : 0;
             avail = ld_volatile(&ring.ctrl[0]) - tail;
             avail = shfl(avail, 0);
             if (avail) break;
-            spin_long();
+            if (ring.mbar) mbar_try_wait((uint64_t*)&ring.ctrl[10], pubs & 1u, 200000);
+            else spin_long();
         }
         const uint32_t m = avail < 32 ? avail : 32;
         threadfence_block();
@@ -715,7 +731,10 @@ SB_DEVICE void k1_chain(const BatchDesc& b, uint32_t flags, uint16_t* table, con
     const bool parser = (wid & 1u) == 0;
     const unsigned pt = (wid & 1u) * 32 + lane;                        // thread index within the pair
     uint32_t tail = 0;                // emitter's private ring counter (never reset)
-    if (pt == 0) { ctrl[0] = 0; ctrl[1] = 0; ctrl[6] = 0; ctrl[7] = 0; }
+    if (pt == 0) {
+        ctrl[0] = 0; ctrl[1] = 0; ctrl[6] = 0; ctrl[7] = 0; ctrl[9] = 0;
+        if (ring.mbar) mbar_init((uint64_t*)&ctrl[10], 1);
+    }
     for (;;) {
         if (pt == 0) ctrl[8] = atomic_add(work, 1u);
         bar_sync(bar, 64);                                                 // previous unit fully drained, next one chosen
@@ -765,6 +784,11 @@ SB_DEVICE void k1_compress_body_multi(const BatchDesc& b, uint32_t flags, uint64
     ring.size = K1_RING_GW;
     ring.ev = ring_scratch + ((size_t)block_idx() * (NC + NG) + c) * K1_RING_GW;
     ring.ctrl = ctrl;
+#if defined(K1_MBAR)
+    ring.mbar = true;
+#elif defined(SB_EMU)
+    ring.mbar = (flags & 8u) != 0;
+#endif
     if (NG == 0 || c < NC) k1_chain<false>(b, flags, (uint16_t*)(sm + (size_t)c * K1_TABLE_BYTES), ring, ctrl, work, 1 + c);
     else k1_chain<true>(b, flags, gtables + ((size_t)block_idx() * NG + (c - NC)) * (K1_TABLE_BYTES / 2), ring, ctrl, work, 1 + c);
 }

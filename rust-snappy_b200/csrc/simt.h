@@ -66,7 +66,12 @@ SB_DEVICE uint32_t reduce_add(uint32_t v) { return __reduce_add_sync(SB_FULL, v)
 SB_DEVICE uint32_t reduce_max(uint32_t v) { return __reduce_max_sync(SB_FULL, v); }
 // polite spin-wait hint inside producer/consumer polling loops
 SB_DEVICE void spin() { __nanosleep(32); }
-SB_DEVICE void spin_long() { __nanosleep(1500); }   // consumer side: latency does not matter, issue slots do
+// consumer side: latency does not matter, issue slots do. ncu showed one NANOSLEEP(1500) lasting only ~65 cycles here
+// (r1_k1_final_12chains: the poll loop was 55% of all issued instructions), hence several back to back.
+SB_DEVICE void spin_long() {
+#pragma unroll
+    for (int i = 0; i < 8; i++) __nanosleep(1000);
+}
 SB_DEVICE uint32_t ld_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 SB_DEVICE void st_volatile(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
 SB_DEVICE uint64_t ld_volatile64(const uint64_t* p) { return *(const volatile uint64_t*)p; }
@@ -78,6 +83,20 @@ SB_DEVICE uint8_t ldg8(const void* p) { return __ldg((const uint8_t*)p); }
 // streaming (evict-first) 16-byte store for write-once output
 SB_DEVICE void stcs128(void* p, uint4 v) { __stcs((uint4*)p, v); }
 
+// mbarrier in shared memory (8 bytes, 8-aligned): producer arrives, consumer blocks in hardware instead of polling
+SB_DEVICE void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+SB_DEVICE void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+// true once the phase of the given parity has completed; otherwise returns false after a hardware-bounded suspend
+SB_DEVICE bool mbar_try_wait(uint64_t* bar, unsigned parity, unsigned hint_ns) {
+    uint32_t done;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity), "r"(hint_ns) : "memory");
+    return done != 0;
+}
 // write-once output bytes: evict-first in L2 so they do not displace data that is re-read
 SB_DEVICE void st8_stream(uint8_t* p, uint8_t v) { __stcs(p, v); }
 extern __shared__ __align__(128) unsigned char sb_dyn_smem[];

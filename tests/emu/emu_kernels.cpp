@@ -8,7 +8,7 @@
 struct K1Args { sb_batch b; uint32_t flags; uint64_t* rings; uint16_t* gtables; uint32_t* work; };
 static void k1_entry(void* a) {
     K1Args* x = (K1Args*)a;
-    if (x->flags & 0x400u) { sbk::k1_compress_body_multi<7, 4>(x->b, x->flags & 0xFFu, x->rings, x->gtables, x->work); return; }   // hybrid: 7 smem + 4 global tables
+    if (x->flags & 0x400u) { sbk::k1_compress_body_multi<7, 4>(x->b, (x->flags & 0xFFu) | ((x->flags & 0x800u) ? 8u : 0u), x->rings, x->gtables, x->work); return; }   // hybrid; 0x800 = mbarrier wake-up: 7 smem + 4 global tables
     if (x->flags & 0x200u) { sbk::k1_compress_body_multi<7, 0>(x->b, x->flags & 0xFFu, x->rings, x->gtables, x->work); return; }
     const bool gw = x->flags & 0x100u;
     const unsigned np = (x->flags >> 12) & 7u, f = x->flags & 0xFFu;

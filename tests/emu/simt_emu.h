@@ -197,6 +197,14 @@ SB_DEVICE uint4 ldg128(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }
 SB_DEVICE uint8_t ldg8(const void* p) { return *(const uint8_t*)p; }
 SB_DEVICE void stcs128(void* p, uint4 v) { memcpy(p, &v, 16); }
 SB_DEVICE void st8_stream(uint8_t* p, uint8_t v) { *p = v; }
+// mbarrier model: the 8 bytes hold the number of completed phases (expected arrival count 1)
+SB_DEVICE void mbar_init(uint64_t* bar, unsigned) { *(volatile uint64_t*)bar = 0; }
+SB_DEVICE void mbar_arrive(uint64_t* bar) { *(volatile uint64_t*)bar = *(volatile uint64_t*)bar + 1; }
+SB_DEVICE bool mbar_try_wait(uint64_t* bar, unsigned parity, unsigned) {
+    if (((*(volatile uint64_t*)bar) & 1u) != parity) return true;
+    sbemu::yield();
+    return ((*(volatile uint64_t*)bar) & 1u) != parity;
+}
 
 SB_DEVICE unsigned char* smem() { return sbemu::g_cur->blk->smem; }
 

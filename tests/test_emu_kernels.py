@@ -88,6 +88,12 @@ def test_k1_adversarial_blocks_all_layouts(oracle, mode):
     assert [i for i, (c, u) in enumerate(zip(got, units)) if c != oracle.compress(u)] == []
 
 
+def test_k1_mbarrier_wakeup(oracle):
+    """Experimental emitter wake-up through an mbarrier (-DK1_MBAR build) instead of sleep-polling."""
+    units = adversarial_blocks()[:16] + [corpus("alice29.txt")[:65536], corpus("kppkn.gtb")[:65536], b"", b"ab"]
+    assert emu.compress_units(units, hybrid=True, mbar=True) == [oracle.compress(u) for u in units]
+
+
 def test_k1_pipelined_parsers(oracle):
     """The NP=2 token-passing variant (kept behind SNAPB200_K1_NP) stays bit-exact."""
     units = adversarial_blocks()[:12] + [corpus("alice29.txt")[:65536], corpus("html")[:65536]]
