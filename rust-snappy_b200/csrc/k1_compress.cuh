@@ -154,6 +154,18 @@ struct K1State {
 };
 
 #define K1_HASH(x) (((uint32_t)(x) * 0x1E35A7BDu) >> shift)
+// Experimental (-DK1_GT_SPEC, not measured on hardware yet): chains whose table lives in L2 read the NEXT window's
+// slots before the current window commits, fetch candidates for those values and re-read the slots afterwards, so the
+// two L2 round trips of a probe overlap; a slot that moved in between costs one more candidate fetch.
+#if defined(SB_EMU)
+static bool g_k1_gt_spec = false;                      // set by the test harness
+static unsigned long g_k1_spec_stat[2] = {0, 0};       // speculated windows, of which had to fetch candidates again
+#define K1_GT_SPEC_ON g_k1_gt_spec
+#elif defined(K1_GT_SPEC)
+#define K1_GT_SPEC_ON true
+#else
+#define K1_GT_SPEC_ON false
+#endif
 
 // after a copy ends at e: `if s >= s_limit return` else insert e-1 (:275-295)
 SB_DEVICE void k1_preinsert(const uint8_t* win, uint16_t* table, unsigned shift, uint32_t s_limit, uint32_t e) {
@@ -275,7 +287,9 @@ SB_DEVICE uint32_t k1_double(uint32_t E, bool eq, uint32_t L) {
     return M;
 }
 
-SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w, const K1Seq* seq K1_PROF_ARGS) {
+template <bool SPEC = false>
+SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w, const K1Seq* seq K1_PROF_ARGS,
+                        uint32_t spec_c = 0, uint32_t spec_i0 = 0) {
     const uint32_t p = w + lane_id();
     K1Pre r;
     const uintptr_t aa = (uintptr_t)(win + p);
@@ -285,11 +299,31 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
     else { const K1Seq q = k1_fetch_seq(win, w); a0 = q.a0; a1 = q.a1; a2 = q.a2; a3 = q.a3; a4 = q.a4; }
     const uint32_t cur = funnel_r(a0, a1, ash);
     r.h = K1_HASH(cur);
-    r.c = table[r.h];
-    const uintptr_t ba = (uintptr_t)(win + r.c);
-    const uint32_t* bw = (const uint32_t*)(ba & ~(uintptr_t)3);
-    const unsigned bsh = (unsigned)(ba & 3u) * 8;
-    const uint32_t b0 = bw[0], b1 = bw[1], b2 = bw[2], b3 = bw[3], b4 = bw[4];
+    uint32_t b0, b1, b2, b3, b4;
+    unsigned bsh;
+    if (SPEC) {
+        // candidate words for the slot value seen before the previous commit, in flight together with the re-read
+        uintptr_t ba = (uintptr_t)(win + spec_c);
+        const uint32_t* bw = (const uint32_t*)(ba & ~(uintptr_t)3);
+        b0 = bw[0]; b1 = bw[1]; b2 = bw[2]; b3 = bw[3]; b4 = bw[4];
+        r.c = table[r.h];
+        const bool moved = any(lane_id() >= spec_i0 && r.c != spec_c);   // lanes before the entry position do not matter
+#if defined(SB_EMU)
+        if (lane_id() == 0) { g_k1_spec_stat[0]++; g_k1_spec_stat[1] += moved ? 1 : 0; }
+#endif
+        if (moved) {                                             // a slot moved: fetch again from the current values
+            ba = (uintptr_t)(win + r.c);
+            bw = (const uint32_t*)(ba & ~(uintptr_t)3);
+            b0 = bw[0]; b1 = bw[1]; b2 = bw[2]; b3 = bw[3]; b4 = bw[4];
+        }
+        bsh = (unsigned)((uintptr_t)(win + r.c) & 3u) * 8;
+    } else {
+        r.c = table[r.h];
+        const uintptr_t ba = (uintptr_t)(win + r.c);
+        const uint32_t* bw = (const uint32_t*)(ba & ~(uintptr_t)3);
+        bsh = (unsigned)(ba & 3u) * 8;
+        b0 = bw[0]; b1 = bw[1]; b2 = bw[2]; b3 = bw[3]; b4 = bw[4];
+    }
     r.eq = cur == funnel_r(b0, b1, bsh);
     // match length, branch-free: bytes 4..15 of both sides, first differing byte wins
     {
@@ -477,6 +511,7 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
     uint32_t my = k;
     K1State lst;                                                   // NP == 1: parse state kept in registers
     lst.s = 1; lst.skip = 32; lst.rematch = false;
+    uint32_t spec_c = 0, spec_w = 0xFFFFFFFFu;                     // speculative slot values of the next window (K1_GT_SPEC)
     bool first = (k == 0);                                         // warp 0 starts with the token
     for (;;) {
         // probe ahead (stale table) while the token is elsewhere
@@ -525,8 +560,14 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
                     K1Seq nxt = seq;
                     if (NP == 1 && w + 100 < n) nxt = k1_fetch_seq(win, w + 32);   // issue next window's loads now
                     K1_TICK(0);                                      // [0] loop top / state checks / prefetch issue
-                    pre = k1_eval(win, table, shift, w, &seq K1_PROF_PASS);
+                    if (NP == 1 && GT && K1_GT_SPEC_ON && spec_w == w) pre = k1_eval<true>(win, table, shift, w, &seq K1_PROF_PASS, spec_c, st.s - w);
+                    else pre = k1_eval(win, table, shift, w, &seq K1_PROF_PASS);
                     seq = nxt;
+                    if (NP == 1 && GT && K1_GT_SPEC_ON && seq.w == w + 32) {
+                        const unsigned nsh = (unsigned)((uintptr_t)(win + seq.w + lane) & 3u) * 8;
+                        spec_c = table[K1_HASH(funnel_r(seq.a0, seq.a1, nsh))];   // as of BEFORE this window's commit
+                        spec_w = seq.w;
+                    }
                 }
                 ok = k1_finish<GT>(win, n, table, shift, s_limit, st, ring, prod, pre, NP == 1 ? &seq : nullptr K1_PROF_PASS);
             }

@@ -21,6 +21,7 @@ extern "C" {
 
 int emu_compress_batch(const sb_batch* b, uint32_t flags, unsigned grid) {
     K1Args a{*b, flags, nullptr, nullptr, nullptr};
+    sbk::g_k1_gt_spec = (flags & 0x8000u) != 0 && (flags & 0x600u) != 0;   // only meaningful for the multi-chain layouts
     if (flags & 0x600u) {
         const unsigned ng = (flags & 0x400u) ? 4 : 0;
         std::vector<uint64_t> rings((size_t)grid * (7 + ng) * sbk::K1_RING_GW, 0xCDCDCDCDCDCDCDCDull);
@@ -36,6 +37,8 @@ int emu_compress_batch(const sb_batch* b, uint32_t flags, unsigned grid) {
     sbemu::launch(grid, ((np < 1 ? 1 : np > 3 ? 3 : np) + 1) * 32, sbk::K1_SMEM_BYTES, k1_entry, &a);
     return 0;
 }
+
+void emu_k1_spec_stat(unsigned long* out) { out[0] = sbk::g_k1_spec_stat[0]; out[1] = sbk::g_k1_spec_stat[1]; }
 
 int emu_decompress_batch(const sb_batch* b, unsigned grid, unsigned block) {
     sb_batch c = *b;

@@ -94,6 +94,12 @@ def test_k1_mbarrier_wakeup(oracle):
     assert emu.compress_units(units, hybrid=True, mbar=True) == [oracle.compress(u) for u in units]
 
 
+def test_k1_speculative_slot_reads(oracle):
+    """Experimental -DK1_GT_SPEC path: L2-table chains read the next window's slots before the commit and revalidate."""
+    units = adversarial_blocks() + [corpus("alice29.txt")[:65536], corpus("html")[:65536], corpus("urls.10K")[:65536]]
+    assert emu.compress_units(units, hybrid=True, gt_spec=True) == [oracle.compress(u) for u in units]
+
+
 def test_k1_pipelined_parsers(oracle):
     """The NP=2 token-passing variant (kept behind SNAPB200_K1_NP) stays bit-exact."""
     units = adversarial_blocks()[:12] + [corpus("alice29.txt")[:65536], corpus("html")[:65536]]
