@@ -98,7 +98,10 @@ typedef struct sb_batch {
 } sb_batch;
 
 /* Each unit (<= 4 GiB - 1) becomes one raw stream exactly as Encoder::compress
- * would produce it. Units of <= 65536 bytes are one block per CTA. */
+ * would produce it. Units of <= 65536 bytes are one block per parser/emitter
+ * warp pair (12 pairs per SM). Compress launches share a per-device scratch
+ * (event rings, L2-resident hash tables, work counter): launches issued on
+ * different streams of one device are ordered after each other on the device. */
 int sb_compress_batch_device(const sb_batch* batch, void* stream, sb_error* err);
 /* Each unit is one raw stream; statuses[i] carries the reference's error. */
 int sb_decompress_batch_device(const sb_batch* batch, void* stream, sb_error* err);
