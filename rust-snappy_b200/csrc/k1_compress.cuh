@@ -160,6 +160,7 @@ struct K1State {
 #if defined(SB_EMU)
 static bool g_k1_gt_spec = false;                      // set by the test harness
 static unsigned long g_k1_spec_stat[2] = {0, 0};       // speculated windows, of which had to fetch candidates again
+static unsigned long g_k1_w32_stat[3] = {0, 0, 0};     // fast steps, bytes they resolved, windows replayed serially
 #define K1_GT_SPEC_ON g_k1_gt_spec
 #elif defined(K1_GT_SPEC)
 #define K1_GT_SPEC_ON true
@@ -569,7 +570,13 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
                         spec_w = seq.w;
                     }
                 }
+#if defined(SB_EMU)
+                const uint32_t s_before = st.s;
+#endif
                 ok = k1_finish<GT>(win, n, table, shift, s_limit, st, ring, prod, pre, NP == 1 ? &seq : nullptr K1_PROF_PASS);
+#if defined(SB_EMU)
+                if (lane == 0) { if (ok) { g_k1_w32_stat[0]++; g_k1_w32_stat[1] += st.s - s_before; } else g_k1_w32_stat[2]++; }
+#endif
             }
             if (!ok) { K1_TICK(8); finished = k1_serial(win, n, table, shift, s_limit, st, w + 32, ring, prod); K1_TICK(9); }   // [9] serial path
             else finished = false;
@@ -755,6 +762,10 @@ SB_DEVICE void k1_compress_body(const BatchDesc& b, uint32_t flags) {
     }
 }
 
+}  // namespace sbk
+#include "k1_wide.cuh"   // experimental 64-position step (off unless -DK1_W64)
+namespace sbk {
+
 // One CTA per SM hosting NC + NG independent (parser, emitter) warp pairs. NC hash tables fill
 // the SM's shared memory (7 x 32KB); NG further chains keep their table in an L2-resident global
 // scratch (`gtables`, 32KB per chain): their probe/commit pays L2 latency, so each runs slower
@@ -800,7 +811,10 @@ SB_DEVICE void k1_chain(const BatchDesc& b, uint32_t flags, uint16_t* table, con
         }
         bar_sync(bar, 64);
         if (parser) {
-            if (n >= 17) k1_parse_pipelined<1, GT>(in, n, table, ring, ctrl, 0);   // (:140-150)
+            if (n >= 17) {                                                 // (:140-150)
+                if (!GT && K1_W64_ON) k1_parse64(in, n, table, ring, ctrl);
+                else k1_parse_pipelined<1, GT>(in, n, table, ring, ctrl, 0);
+            }
             else {                                                         // tiny block: one literal (:140-146)
                 K1Prod prod;
                 prod.head = ctrl[6]; prod.published = ctrl[7]; prod.tail_seen = 0;

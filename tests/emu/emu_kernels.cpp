@@ -21,7 +21,8 @@ extern "C" {
 
 int emu_compress_batch(const sb_batch* b, uint32_t flags, unsigned grid) {
     K1Args a{*b, flags, nullptr, nullptr, nullptr};
-    sbk::g_k1_gt_spec = (flags & 0x8000u) != 0 && (flags & 0x600u) != 0;   // only meaningful for the multi-chain layouts
+    sbk::g_k1_gt_spec = (flags & 0x8000u) != 0 && (flags & 0x600u) != 0;
+    sbk::g_k1_w64 = (flags & 0x10000u) != 0 && (flags & 0x600u) != 0;      // 64-position step (shared-memory-table chains)   // only meaningful for the multi-chain layouts
     if (flags & 0x600u) {
         const unsigned ng = (flags & 0x400u) ? 4 : 0;
         std::vector<uint64_t> rings((size_t)grid * (7 + ng) * sbk::K1_RING_GW, 0xCDCDCDCDCDCDCDCDull);
@@ -38,6 +39,7 @@ int emu_compress_batch(const sb_batch* b, uint32_t flags, unsigned grid) {
     return 0;
 }
 
+void emu_k1_step_stat(unsigned long* out) { for (int i = 0; i < 3; i++) { out[i] = sbk::g_k1_w32_stat[i]; out[3 + i] = sbk::g_k1_w64_stat[i]; } }
 void emu_k1_spec_stat(unsigned long* out) { out[0] = sbk::g_k1_spec_stat[0]; out[1] = sbk::g_k1_spec_stat[1]; }
 
 int emu_decompress_batch(const sb_batch* b, unsigned grid, unsigned block) {

@@ -1,5 +1,7 @@
 # A/B the product library against experimental builds on one GPU (run under gpurun; build the variants first, here):
 #   bash tools/build_variant.sh mbar -DK1_MBAR      # emitters woken through an mbarrier instead of sleep-polling
+#   bash tools/build_variant.sh spec -DK1_GT_SPEC   # L2-table chains: speculative slot reads
+#   bash tools/build_variant.sh w64 -DK1_W64        # 64 positions per parser step on the shared-memory-table chains
 # usage: bash tools/ab_variants.sh [suffix ...]      (each suffix = rust-snappy_b200/libsnapb200_<suffix>.so)
 mkdir -p gpurun_out
 run() {
