@@ -158,11 +158,8 @@ SB_DEVICE bool k1_finish64(const uint8_t* win, uint32_t n, uint16_t* table, unsi
     if (t1) interior |= k1_below64(32 + lane + L1 - 1) & ~k1_below64(32 + lane + 1);
     const uint64_t I = (uint64_t)reduce_or((uint32_t)interior) | ((uint64_t)reduce_or((uint32_t)(interior >> 32)) << 32);
     const uint64_t C = (~0ull << i0) & ~I;
-    // copy-end inserts (e-1) are write-only
-    uint64_t pre_bits = 0;
-    if (t0 && lane + L0 - 1 < 64) pre_bits |= 1ull << (lane + L0 - 1);
-    if (t1 && 32 + lane + L1 - 1 < 64) pre_bits |= 1ull << (32 + lane + L1 - 1);
-    const uint64_t PRE = (uint64_t)reduce_or((uint32_t)pre_bits) | ((uint64_t)reduce_or((uint32_t)(pre_bits >> 32)) << 32);
+    // copy-end inserts (e-1) are write-only; e-1 is the position right after a copy's interior (which is never empty)
+    const uint64_t PRE = (I << 1) & ~I;
     const uint32_t p0 = w + lane, p1 = w + 32 + lane;
 #ifdef SB_EMU_TRACE
     if (lane == 0) fprintf(stderr, "win64 w=%u i0=%u rm=%d skip=%u E=%016llx f=%u CS=%016llx C=%016llx\n", w, i0, (int)st.rematch, st.skip,
