@@ -130,27 +130,37 @@ SB_DEVICE bool k1_finish64(const uint8_t* win, uint32_t n, uint16_t* table, unsi
         const uint32_t probes = f < 64 ? f - i0 + 1 : 64 - i0;
         if (st.skip + probes > 64) return false;
     }
-    // ---- walk the taken copies (every lane computes the same chain)
-    uint64_t CS = 0, longmask = pre.longs;
-    uint32_t e_last = 0;
+    // ---- per entry, in parallel: where the parse goes after a copy taken here (next hit at/after its end, 64 = leaves
+    // the window or no more hits), whether the scan run behind it leaves stride 1, whether its length is still open
+    auto hop = [&](uint32_t pos, uint32_t len, bool lng) -> uint32_t {
+        const uint32_t e = pos + len;
+        uint32_t nx = 64, viol = 0;
+        if (e < 64) {
+            const uint64_t m = E >> e;
+            if (m) nx = e + (uint32_t)(ffsll(m) - 1);
+            viol = (nx != e && (nx < 64 ? nx - e : 63 - e) > 32) ? 1u : 0u;
+        }
+        return nx | (viol << 7) | ((lng ? 1u : 0u) << 8);
+    };
+    uint32_t pk0 = hop(lane, L0, (pre.longs >> lane) & 1ull), pk1 = hop(32 + lane, L1, (pre.longs >> (32 + lane)) & 1ull);
+    // ---- walk the taken copies: one shuffle per hop (every lane follows the same chain)
+    uint64_t CS = 0;
+    uint32_t last = 64;
     for (uint32_t cur = f; cur < 64;) {
-        uint32_t Lc = k1_pick64(L0, L1, cur);
-        if ((longmask >> cur) & 1ull) {                          // >= 16 bytes: extend cooperatively to the exact end
+        uint32_t pk = k1_pick64(pk0, pk1, cur);
+        if (pk & 0x100u) {                                       // >= 16 bytes: extend cooperatively to the exact end
             const uint32_t cj = k1_pick64(pre.c[0], pre.c[1], cur);
             const uint32_t pj = w + cur;
-            Lc = k1_extend(win, n, pj + 16, cj + 16) - pj;
-            if (lane == (cur & 31u)) { if (cur < 32) L0 = Lc; else L1 = Lc; }
-            longmask &= ~(1ull << cur);
+            const uint32_t Lc = k1_extend(win, n, pj + 16, cj + 16) - pj;
+            pk = hop(cur, Lc, false);
+            if (lane == (cur & 31u)) { if (cur < 32) { L0 = Lc; pk0 = pk; } else { L1 = Lc; pk1 = pk; } }
         }
+        if (pk & 0x80u) return false;                            // the scan run after this copy leaves stride 1
         CS |= 1ull << cur;
-        const uint32_t e = cur + Lc;
-        e_last = e;
-        if (e >= 64) break;
-        const uint64_t m = E >> e;
-        const uint32_t nx = m ? e + (uint32_t)(ffsll(m) - 1) : 64;
-        if (nx != e && (nx < 64 ? nx - e : 63 - e) > 32) return false;   // the scan run after this copy leaves stride 1
-        cur = nx;
+        last = cur;
+        cur = pk & 0x7Fu;
     }
+    const uint32_t e_last = last < 64 ? last + k1_pick64(L0, L1, last) : 0;
     // ---- inserted positions = entry..63 minus copy interiors [q+1, e-2]
     const bool t0 = (CS >> lane) & 1ull, t1 = (CS >> (32 + lane)) & 1ull;
     uint64_t interior = 0;
