@@ -24,7 +24,7 @@ namespace sbk {
 
 #if defined(SB_EMU)
 static bool g_k1_w64 = false;                          // set by the test harness
-static unsigned long g_k1_w64_stat[3] = {0, 0, 0};     // fast steps, bytes they resolved, windows replayed serially
+static unsigned long g_k1_w64_stat[5] = {0, 0, 0, 0, 0};   // fast steps, bytes resolved, serial replays, clash resolutions, cuts
 #define K1_W64_ON g_k1_w64
 #elif defined(K1_W64)
 #define K1_W64_ON true
@@ -87,17 +87,23 @@ SB_DEVICE K1Pre64 k1_eval64(const uint8_t* win, const uint16_t* table, unsigned 
 // inserts (never victims); `old`: the slot value to put back when the commit has to be redone; `limit`: lanes at or
 // above it are not part of the step (a victim found earlier). Returns the cut: the first victim lane of this half
 // (`limit` if none); on return the table holds exactly the inserts of lanes below the cut, last writer of a slot wins.
+// `peek_h` / `peek`: a slot every lane wants to read as of AFTER this commit (issued together with the verify read).
 SB_DEVICE uint32_t k1_commit_half(uint16_t* table, uint32_t h, uint32_t p, uint32_t old, uint32_t ins, uint32_t pre,
-                                  uint32_t limit) {
+                                  uint32_t limit, uint32_t peek_h, uint32_t& peek) {
     const unsigned lane = lane_id();
     const uint32_t keep0 = ins & (limit >= 32 ? 0xFFFFFFFFu : ((1u << limit) - 1u));
     const bool my = (keep0 >> lane) & 1u;
     syncwarp();                                                  // every probe read precedes the commit
     if (my) table[h] = (uint16_t)p;
     syncwarp();
-    const bool clash = my && table[h] != (uint16_t)p;
+    const uint32_t seen = table[h];
+    peek = table[peek_h];
+    const bool clash = my && seen != (uint16_t)p;
     uint32_t cut = limit;
     if (any(clash)) {
+#if defined(SB_EMU)
+        if (lane == 0) g_k1_w64_stat[3]++;
+#endif
         const uint32_t same = match_any(my ? h : 0xFFFF0000u | lane);
         const bool victim = my && !((pre >> lane) & 1u) && (same & keep0 & ((1u << lane) - 1u)) != 0;
         const uint32_t vm = ballot(victim);
@@ -108,6 +114,7 @@ SB_DEVICE uint32_t k1_commit_half(uint16_t* table, uint32_t h, uint32_t p, uint3
         const uint32_t keep = keep0 & (cut >= 32 ? 0xFFFFFFFFu : ((1u << cut) - 1u));
         if (((keep >> lane) & 1u) && (same & keep & ~((2u << lane) - 1u)) == 0) table[h] = (uint16_t)p;
         syncwarp();
+        peek = table[peek_h];
     }
     return cut;
 }
@@ -176,13 +183,15 @@ SB_DEVICE bool k1_finish64(const uint8_t* win, uint32_t n, uint16_t* table, unsi
                            (unsigned long long)E, f, (unsigned long long)CS, (unsigned long long)C);
 #endif
     // ---- commit half 0, find half 1's victims of half 0's inserts, commit half 1
-    uint32_t cut = k1_commit_half(table, pre.h[0], p0, pre.c[0], (uint32_t)C, (uint32_t)PRE, 32);
+    uint32_t c1, unused;
+    uint32_t cut = k1_commit_half(table, pre.h[0], p0, pre.c[0], (uint32_t)C, (uint32_t)PRE, 32, pre.h[1], c1);
     if (cut >= 32) {
-        const uint32_t c1 = table[pre.h[1]];                      // after half 0's commit
+        // c1 = half 1's slots after half 0's commit: a probed lane whose slot moved should have seen a candidate
+        // from half 0 -> victim
         const bool probed1 = ((C >> (32 + lane)) & 1ull) && !((PRE >> (32 + lane)) & 1ull);
-        const uint32_t moved = ballot(probed1 && c1 != pre.c[1]);   // should have seen a candidate from half 0
+        const uint32_t moved = ballot(probed1 && c1 != pre.c[1]);
         const uint32_t limit = moved ? (uint32_t)(ffs(moved) - 1) : 32;
-        cut = 32 + k1_commit_half(table, pre.h[1], p1, c1, (uint32_t)(C >> 32), (uint32_t)(PRE >> 32), limit);
+        cut = 32 + k1_commit_half(table, pre.h[1], p1, c1, (uint32_t)(C >> 32), (uint32_t)(PRE >> 32), limit, pre.h[1], unused);
     }
     // ---- events of the accepted copies
     CS &= k1_below64(cut);
@@ -198,6 +207,9 @@ SB_DEVICE bool k1_finish64(const uint8_t* win, uint32_t n, uint16_t* table, unsi
     }
     // ---- exit state
     if (cut < 64) {                                              // cut at a victim: restart the window there
+#if defined(SB_EMU)
+        if (lane == 0) g_k1_w64_stat[4]++;
+#endif
         if (ncopy) {
             const uint32_t lastc = (CS >> 32) ? 63 - clz((uint32_t)(CS >> 32)) : 31 - clz((uint32_t)CS);
             const uint32_t e2 = lastc + k1_pick64(L0, L1, lastc);     // <= cut: a victim is never inside a copy

@@ -39,7 +39,7 @@ int emu_compress_batch(const sb_batch* b, uint32_t flags, unsigned grid) {
     return 0;
 }
 
-void emu_k1_step_stat(unsigned long* out) { for (int i = 0; i < 3; i++) { out[i] = sbk::g_k1_w32_stat[i]; out[3 + i] = sbk::g_k1_w64_stat[i]; } }
+void emu_k1_step_stat(unsigned long* out) { for (int i = 0; i < 3; i++) { out[i] = sbk::g_k1_w32_stat[i]; out[3 + i] = sbk::g_k1_w64_stat[i]; } out[6] = sbk::g_k1_w64_stat[3]; out[7] = sbk::g_k1_w64_stat[4]; }
 void emu_k1_spec_stat(unsigned long* out) { out[0] = sbk::g_k1_spec_stat[0]; out[1] = sbk::g_k1_spec_stat[1]; }
 
 int emu_decompress_batch(const sb_batch* b, unsigned grid, unsigned block) {
