@@ -24,12 +24,21 @@ namespace sbk {
 
 #if defined(SB_EMU)
 static bool g_k1_w64 = false;                          // set by the test harness
+static bool g_k1_w64_aligned = false;                  // ... windows on 64-byte boundaries instead of starting at the parse position
+#define K1_W64_ALIGNED_ON g_k1_w64_aligned
 static unsigned long g_k1_w64_stat[5] = {0, 0, 0, 0, 0};   // fast steps, bytes resolved, serial replays, clash resolutions, cuts
 #define K1_W64_ON g_k1_w64
 #elif defined(K1_W64)
 #define K1_W64_ON true
 #else
 #define K1_W64_ON false
+#endif
+#if !defined(SB_EMU)
+#if defined(K1_W64_ALIGNED)
+#define K1_W64_ALIGNED_ON true
+#else
+#define K1_W64_ALIGNED_ON false
+#endif
 #endif
 
 struct K1Seq64 { uint32_t a[2][5]; uint32_t w; };
@@ -122,9 +131,9 @@ SB_DEVICE uint32_t k1_commit_half(uint16_t* table, uint32_t h, uint32_t p, uint3
 // One 64-position step from a current probe. Returns false (state and table untouched) when the window has to be
 // replayed serially (a scan run inside it leaves stride 1).
 SB_DEVICE bool k1_finish64(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
-                           K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre64& pre, const K1Seq64& nxt) {
+                           K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre64& pre, const K1Seq64& nxt, uint32_t w) {
     const unsigned lane = lane_id();
-    const uint32_t w = st.s & ~63u, i0 = st.s - w;
+    const uint32_t i0 = st.s - w;                                // 0 unless windows are kept on 64-byte boundaries
     const uint64_t E = pre.E;
     uint32_t L0 = pre.L[0], L1 = pre.L[1];
     // ---- entry: rematch probe at i0 or scan from i0 -> first hit at/after i0
@@ -265,7 +274,9 @@ SB_DEVICE void k1_parse64(const uint8_t* win, uint32_t n, uint16_t* table, const
 #pragma unroll
     for (int k = 0; k < 5; k++) { seq.a[0][k] = 0; seq.a[1][k] = 0; }
     for (;;) {
-        const uint32_t w = st.s & ~63u;
+        // A window starts where the parse stands (tools/sim_window_width.py: 60 bytes per step on text against 52 for
+        // windows on 64-byte boundaries); the prefetch guesses that the next one starts at w + 64.
+        const uint32_t w = K1_W64_ALIGNED_ON ? (st.s & ~63u) : st.s;
         // highest read of a step: aligned word of w+63 plus five words -> w + 82 < n
         const bool fast = w + 68 < s_limit && (st.rematch || st.skip < 64);
         bool finished;
@@ -280,7 +291,7 @@ SB_DEVICE void k1_parse64(const uint8_t* win, uint32_t n, uint16_t* table, const
 #if defined(SB_EMU)
                 const uint32_t s_before = st.s;
 #endif
-                ok = k1_finish64(win, n, table, shift, s_limit, st, ring, prod, pre, seq);
+                ok = k1_finish64(win, n, table, shift, s_limit, st, ring, prod, pre, seq, w);
 #if defined(SB_EMU)
                 if (lane == 0) { if (ok) { g_k1_w64_stat[0]++; g_k1_w64_stat[1] += st.s - s_before; } else g_k1_w64_stat[2]++; }
 #endif

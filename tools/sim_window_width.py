@@ -76,3 +76,31 @@ for name in ["alice29.txt","html","urls.10K","geo.protodata","kppkn.gtb","lcet10
         t,nw=steps(pr,cp,len(d),W)
         out+= [f'W{W}: steps {t} (windows {nw}) bytes/step {len(d)/t:.1f}']
     print(*out)
+
+
+def steps_unaligned(probes, n, W):
+    """windows start exactly where the previous step stopped (no alignment): [s, s+W)"""
+    total = 0
+    i = 0
+    P = len(probes)
+    while i < P:
+        s = probes[i][0]
+        total += 1
+        j = i
+        nxt = None
+        while j < P and probes[j][0] < s + W:
+            p, c, st = probes[j]
+            if j > i and c >= s and c < p:      # victim: cut here
+                nxt = j
+                break
+            j += 1
+        i = nxt if nxt is not None else j
+    return total
+
+
+if __name__ == "__main__":
+    print("--- unaligned windows (bytes per step)")
+    for name in ["alice29.txt", "html", "urls.10K", "kppkn.gtb"]:
+        d = corpus(name)[:65536]
+        pr, cp = parse(d)
+        print(name, *[f"W{W}: {len(d) / steps_unaligned(pr, len(d), W):.1f}" for W in (32, 64, 128)])
