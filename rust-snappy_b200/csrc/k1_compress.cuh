@@ -157,6 +157,17 @@ struct K1State {
 // Experimental (-DK1_GT_SPEC, not measured on hardware yet): chains whose table lives in L2 read the NEXT window's
 // slots before the current window commits, fetch candidates for those values and re-read the slots afterwards, so the
 // two L2 round trips of a probe overlap; a slot that moved in between costs one more candidate fetch.
+// Experimental (-DK1_UNALIGNED, not measured on hardware yet): the single-parser loop starts each 32-position window
+// where the parse stands instead of on a 32-byte boundary (tools/sim_window_width.py: 33.5 bytes per step on text
+// against 30.3); the prefetch then guesses that the next window starts at w + 32.
+#if defined(SB_EMU)
+static bool g_k1_unaligned = false;                    // set by the test harness
+#define K1_UNALIGNED_ON g_k1_unaligned
+#elif defined(K1_UNALIGNED)
+#define K1_UNALIGNED_ON true
+#else
+#define K1_UNALIGNED_ON false
+#endif
 #if defined(SB_EMU)
 static bool g_k1_gt_spec = false;                      // set by the test harness
 static unsigned long g_k1_spec_stat[2] = {0, 0};       // speculated windows, of which had to fetch candidates again
@@ -351,9 +362,10 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
 // full L2 round trip there, so slot clashes are found by comparing hashes across lanes.
 template <bool GT>
 SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
-                         K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre& pre, const K1Seq* nxt K1_PROF_ARGS) {
+                         K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre& pre, const K1Seq* nxt K1_PROF_ARGS,
+                         uint32_t wbase = 0xFFFFFFFFu) {
     const unsigned lane = lane_id();
-    const uint32_t w = st.s & ~31u, i0 = st.s - w, p = w + lane;
+    const uint32_t w = wbase != 0xFFFFFFFFu ? wbase : (st.s & ~31u), i0 = st.s - w, p = w + lane;
     const uint32_t h = pre.h, c = pre.c, E = pre.E;
     const bool eq = pre.eq;
     uint32_t L = pre.L;
@@ -535,7 +547,7 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
             // single parser: state lives in registers, only the producer counters persist across units
             if (my == 0) { lst.s = 1; lst.skip = 32; lst.rematch = false; prod.head = ld_volatile(&ctrl[6]); prod.published = ld_volatile(&ctrl[7]); }
             st = lst;
-            my = st.s >> 5; w = my * 32;
+            my = st.s >> 5; w = K1_UNALIGNED_ON ? st.s : my * 32;
         } else {
             const uint32_t t = ld_volatile(&ctrl[2]);
             if (t == K1_DONE) { bar_arrive(bar_next, 64); return; }
@@ -573,7 +585,8 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
 #if defined(SB_EMU)
                 const uint32_t s_before = st.s;
 #endif
-                ok = k1_finish<GT>(win, n, table, shift, s_limit, st, ring, prod, pre, NP == 1 ? &seq : nullptr K1_PROF_PASS);
+                ok = k1_finish<GT>(win, n, table, shift, s_limit, st, ring, prod, pre, NP == 1 ? &seq : nullptr K1_PROF_PASS,
+                                   (NP == 1 && K1_UNALIGNED_ON) ? w : 0xFFFFFFFFu);
 #if defined(SB_EMU)
                 if (lane == 0) { if (ok) { g_k1_w32_stat[0]++; g_k1_w32_stat[1] += st.s - s_before; } else g_k1_w32_stat[2]++; }
 #endif

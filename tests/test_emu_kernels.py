@@ -110,6 +110,17 @@ def test_k1_wide_step(oracle, hybrid, aligned):
     assert [i for i, (g, u) in enumerate(zip(got, units)) if g != oracle.compress(u)] == []
 
 
+def test_k1_unaligned_windows(oracle):
+    """Experimental -DK1_UNALIGNED path: 32-position windows that start where the parse stands."""
+    units = adversarial_blocks() + [b"", b"a"] + small_copy_inputs()[::7]
+    for name in ("alice29.txt", "html", "urls.10K", "kppkn.gtb", "fireworks.jpeg"):
+        units += blocks_of(corpus(name))[:2]
+    got = emu.compress_units(units, hybrid=True, unaligned=True, grid=2)
+    assert [i for i, (g, u) in enumerate(zip(got, units)) if g != oracle.compress(u)] == []
+    got = emu.compress_units(units[:40], hybrid=True, unaligned=True, w64=True, gt_spec=True)   # all experiments together
+    assert [i for i, (g, u) in enumerate(zip(got, units[:40])) if g != oracle.compress(u)] == []
+
+
 def test_k1_pipelined_parsers(oracle):
     """The NP=2 token-passing variant (kept behind SNAPB200_K1_NP) stays bit-exact."""
     units = adversarial_blocks()[:12] + [corpus("alice29.txt")[:65536], corpus("html")[:65536]]

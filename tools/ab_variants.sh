@@ -2,6 +2,8 @@
 #   bash tools/build_variant.sh mbar -DK1_MBAR      # emitters woken through an mbarrier instead of sleep-polling
 #   bash tools/build_variant.sh spec -DK1_GT_SPEC   # L2-table chains: speculative slot reads
 #   bash tools/build_variant.sh w64 -DK1_W64        # 64 positions per parser step on the shared-memory-table chains
+#   bash tools/build_variant.sh una -DK1_UNALIGNED  # 32-position windows start where the parse stands
+#   (the flags combine: build_variant.sh all -DK1_W64 -DK1_UNALIGNED -DK1_GT_SPEC -DK1_MBAR)
 # usage: bash tools/ab_variants.sh [suffix ...]      (each suffix = rust-snappy_b200/libsnapb200_<suffix>.so)
 mkdir -p gpurun_out
 run() {
