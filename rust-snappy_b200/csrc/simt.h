@@ -66,12 +66,10 @@ SB_DEVICE uint32_t reduce_add(uint32_t v) { return __reduce_add_sync(SB_FULL, v)
 SB_DEVICE uint32_t reduce_max(uint32_t v) { return __reduce_max_sync(SB_FULL, v); }
 // polite spin-wait hint inside producer/consumer polling loops
 SB_DEVICE void spin() { __nanosleep(32); }
-// consumer side: latency does not matter, issue slots do. ncu showed one NANOSLEEP(1500) lasting only ~65 cycles here
-// (r1_k1_final_12chains: the poll loop was 55% of all issued instructions), hence several back to back.
-SB_DEVICE void spin_long() {
-#pragma unroll
-    for (int i = 0; i < 8; i++) __nanosleep(1000);
-}
+// consumer side: latency matters little, issue slots do. (The per-instruction counts of an ncu --set full capture
+// overstate this poll loop: they come from the instrumented replay, which runs many times longer than the kernel, and
+// polls scale with time; the hardware counter of the same capture puts polling at ~2-3% of issued instructions.)
+SB_DEVICE void spin_long() { __nanosleep(1500); }
 SB_DEVICE uint32_t ld_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 SB_DEVICE void st_volatile(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
 SB_DEVICE uint64_t ld_volatile64(const uint64_t* p) { return *(const volatile uint64_t*)p; }
