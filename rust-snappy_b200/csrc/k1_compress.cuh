@@ -825,7 +825,7 @@ SB_DEVICE void k1_chain(const BatchDesc& b, uint32_t flags, uint16_t* table, con
         bar_sync(bar, 64);
         if (parser) {
             if (n >= 17) {                                                 // (:140-150)
-                if (!GT && K1_W64_ON) k1_parse64(in, n, table, ring, ctrl);
+                if (K1_W64_ON && (!GT || K1_W64_GT_ON)) k1_parse64<GT>(in, n, table, ring, ctrl);
                 else k1_parse_pipelined<1, GT>(in, n, table, ring, ctrl, 0);
             }
             else {                                                         // tiny block: one literal (:140-146)

@@ -33,6 +33,16 @@ static unsigned long g_k1_w64_stat[5] = {0, 0, 0, 0, 0};   // fast steps, bytes 
 #else
 #define K1_W64_ON false
 #endif
+// -DK1_W64_GT: the chains whose table lives in L2 take 64-position steps too; their commit finds slot clashes and
+// victims by comparing hashes across lanes (match.any) BEFORE storing, so it never reads the table back
+#if defined(SB_EMU)
+static bool g_k1_w64_gt = false;
+#define K1_W64_GT_ON g_k1_w64_gt
+#elif defined(K1_W64_GT)
+#define K1_W64_GT_ON true
+#else
+#define K1_W64_GT_ON false
+#endif
 #if !defined(SB_EMU)
 #if defined(K1_W64_ALIGNED)
 #define K1_W64_ALIGNED_ON true
@@ -128,8 +138,54 @@ SB_DEVICE uint32_t k1_commit_half(uint16_t* table, uint32_t h, uint32_t p, uint3
     return cut;
 }
 
+// Commit of a 64-position step without reading the table back (for tables in L2): same-slot groups come from
+// match.any over the hashes, so victims and the cut are known before anything is stored.
+//   C / PRE: inserted positions / write-only copy-end inserts of the step. Returns the cut (64 = whole step accepted);
+//   on return the table holds exactly the inserts below the cut, last writer of a slot wins.
+SB_DEVICE uint32_t k1_commit64_match(uint16_t* table, uint32_t h0, uint32_t h1, uint32_t p0, uint32_t p1, uint64_t C, uint64_t PRE) {
+    const unsigned lane = lane_id();
+    const uint32_t C0 = (uint32_t)C, C1 = (uint32_t)(C >> 32), PRE0 = (uint32_t)PRE, PRE1 = (uint32_t)(PRE >> 32);
+    const bool ins0 = (C0 >> lane) & 1u, ins1 = (C1 >> lane) & 1u;
+    const uint32_t below = (1u << lane) - 1u, above = ~((2u << lane) - 1u);
+    const uint32_t key0 = ins0 ? h0 : (0xFFFF0000u | lane);      // hashes are < 16384: these never match anything
+    // ---- half 0: a probed lane with a lower inserted lane of the same hash is a victim
+    const uint32_t same0 = match_any(key0);
+    const uint32_t v0 = ballot(ins0 && !((PRE0 >> lane) & 1u) && (same0 & C0 & below) != 0);
+    syncwarp();                                                  // every probe read precedes the commit
+    if (v0) {
+        const uint32_t cut0 = ffs(v0) - 1;
+        const uint32_t keep0 = C0 & ((1u << cut0) - 1u);
+        if (((keep0 >> lane) & 1u) && (same0 & keep0 & above) == 0) table[h0] = (uint16_t)p0;
+        syncwarp();
+        return cut0;
+    }
+    // ---- half 1 against half 0's inserts: every (i, j) pair has to sit on two different lanes of one match.any,
+    // which takes four calls (lanes 0-15 / 16-31 of each side, the second pair with half 1's hashes rotated by 16)
+    const bool lo16 = lane < 16;
+    const uint32_t q1s = shfl(h1, lane ^ 16u);
+    const uint32_t mA = match_any(lo16 ? key0 : h1);             // j in 0..15 , i in 16..31 (on its own lane)
+    const uint32_t mB = match_any(lo16 ? h1 : key0);             // j in 16..31, i in 0..15  (on its own lane)
+    const uint32_t mC = match_any(lo16 ? key0 : q1s);            // j in 0..15 , i in 0..15  (on lane i+16)
+    const uint32_t mD = match_any(lo16 ? q1s : key0);            // j in 16..31, i in 16..31 (on lane i-16)
+    const uint32_t moved = ballot(!lo16 && (mA & 0x0000FFFFu) != 0) | ballot(lo16 && (mB & 0xFFFF0000u) != 0) |
+                           (ballot(!lo16 && (mC & 0x0000FFFFu) != 0) >> 16) | (ballot(lo16 && (mD & 0xFFFF0000u) != 0) << 16);
+    // ---- half 1 itself
+    const uint32_t key1 = ins1 ? h1 : (0xFFFF0000u | lane);
+    const uint32_t same1 = match_any(key1);
+    const uint32_t probed1 = C1 & ~PRE1;
+    const uint32_t v1 = ballot(ins1 && !((PRE1 >> lane) & 1u) && (same1 & C1 & below) != 0) | (moved & probed1);
+    const uint32_t cut1 = v1 ? (uint32_t)(ffs(v1) - 1) : 32;
+    if (ins0 && (same0 & C0 & above) == 0) table[h0] = (uint16_t)p0;
+    syncwarp();                                                  // half 1's stores land after half 0's
+    const uint32_t keep1 = C1 & (cut1 >= 32 ? 0xFFFFFFFFu : ((1u << cut1) - 1u));
+    if (((keep1 >> lane) & 1u) && (same1 & keep1 & above) == 0) table[h1] = (uint16_t)p1;
+    syncwarp();
+    return 32 + cut1;
+}
+
 // One 64-position step from a current probe. Returns false (state and table untouched) when the window has to be
 // replayed serially (a scan run inside it leaves stride 1).
+template <bool GT>
 SB_DEVICE bool k1_finish64(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
                            K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre64& pre, const K1Seq64& nxt, uint32_t w) {
     const unsigned lane = lane_id();
@@ -192,15 +248,20 @@ SB_DEVICE bool k1_finish64(const uint8_t* win, uint32_t n, uint16_t* table, unsi
                            (unsigned long long)E, f, (unsigned long long)CS, (unsigned long long)C);
 #endif
     // ---- commit half 0, find half 1's victims of half 0's inserts, commit half 1
-    uint32_t c1, unused;
-    uint32_t cut = k1_commit_half(table, pre.h[0], p0, pre.c[0], (uint32_t)C, (uint32_t)PRE, 32, pre.h[1], c1);
-    if (cut >= 32) {
-        // c1 = half 1's slots after half 0's commit: a probed lane whose slot moved should have seen a candidate
-        // from half 0 -> victim
-        const bool probed1 = ((C >> (32 + lane)) & 1ull) && !((PRE >> (32 + lane)) & 1ull);
-        const uint32_t moved = ballot(probed1 && c1 != pre.c[1]);
-        const uint32_t limit = moved ? (uint32_t)(ffs(moved) - 1) : 32;
-        cut = 32 + k1_commit_half(table, pre.h[1], p1, c1, (uint32_t)(C >> 32), (uint32_t)(PRE >> 32), limit, pre.h[1], unused);
+    uint32_t cut;
+    if (GT) {
+        cut = k1_commit64_match(table, pre.h[0], pre.h[1], p0, p1, C, PRE);
+    } else {
+        uint32_t c1, unused;
+        cut = k1_commit_half(table, pre.h[0], p0, pre.c[0], (uint32_t)C, (uint32_t)PRE, 32, pre.h[1], c1);
+        if (cut >= 32) {
+            // c1 = half 1's slots after half 0's commit: a probed lane whose slot moved should have seen a candidate
+            // from half 0 -> victim
+            const bool probed1 = ((C >> (32 + lane)) & 1ull) && !((PRE >> (32 + lane)) & 1ull);
+            const uint32_t moved = ballot(probed1 && c1 != pre.c[1]);
+            const uint32_t limit = moved ? (uint32_t)(ffs(moved) - 1) : 32;
+            cut = 32 + k1_commit_half(table, pre.h[1], p1, c1, (uint32_t)(C >> 32), (uint32_t)(PRE >> 32), limit, pre.h[1], unused);
+        }
     }
     // ---- events of the accepted copies
     CS &= k1_below64(cut);
@@ -259,6 +320,7 @@ SB_DEVICE bool k1_finish64(const uint8_t* win, uint32_t n, uint16_t* table, unsi
 }
 
 // Single parser warp over 64-position windows; same role as k1_parse_pipelined<1> (k1_compress.cuh).
+template <bool GT>
 SB_DEVICE void k1_parse64(const uint8_t* win, uint32_t n, uint16_t* table, const K1Ring& ring, uint32_t* ctrl) {
     const unsigned lane = lane_id();
     unsigned shift = 24;
@@ -291,7 +353,7 @@ SB_DEVICE void k1_parse64(const uint8_t* win, uint32_t n, uint16_t* table, const
 #if defined(SB_EMU)
                 const uint32_t s_before = st.s;
 #endif
-                ok = k1_finish64(win, n, table, shift, s_limit, st, ring, prod, pre, seq, w);
+                ok = k1_finish64<GT>(win, n, table, shift, s_limit, st, ring, prod, pre, seq, w);
 #if defined(SB_EMU)
                 if (lane == 0) { if (ok) { g_k1_w64_stat[0]++; g_k1_w64_stat[1] += st.s - s_before; } else g_k1_w64_stat[2]++; }
 #endif

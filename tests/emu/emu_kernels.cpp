@@ -24,6 +24,7 @@ int emu_compress_batch(const sb_batch* b, uint32_t flags, unsigned grid) {
     sbk::g_k1_gt_spec = (flags & 0x8000u) != 0 && (flags & 0x600u) != 0;
     sbk::g_k1_w64 = (flags & 0x10000u) != 0 && (flags & 0x600u) != 0;
     sbk::g_k1_w64_aligned = (flags & 0x20000u) != 0;
+    sbk::g_k1_w64_gt = (flags & 0x80000u) != 0;
     sbk::g_k1_unaligned = (flags & 0x40000u) != 0 && (flags & 0x600u) != 0;      // 64-position step (shared-memory-table chains)   // only meaningful for the multi-chain layouts
     if (flags & 0x600u) {
         const unsigned ng = (flags & 0x400u) ? 4 : 0;

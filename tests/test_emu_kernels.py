@@ -100,13 +100,14 @@ def test_k1_speculative_slot_reads(oracle):
     assert emu.compress_units(units, hybrid=True, gt_spec=True) == [oracle.compress(u) for u in units]
 
 
-@pytest.mark.parametrize("hybrid,aligned", [(False, False), (True, False), (False, True)])
-def test_k1_wide_step(oracle, hybrid, aligned):
-    """Experimental -DK1_W64 path: 64 positions per parser step on the shared-memory-table chains."""
+@pytest.mark.parametrize("hybrid,aligned,gt", [(False, False, False), (True, False, False), (False, True, False), (True, False, True)])
+def test_k1_wide_step(oracle, hybrid, aligned, gt):
+    """Experimental -DK1_W64 path: 64 positions per parser step on the shared-memory-table chains
+    (gt: also on the L2-table chains, with the match.any commit of -DK1_W64_GT)."""
     units = adversarial_blocks() + [b"", b"a", RANDOM[0]] + small_copy_inputs()[::7]
     for name in ("alice29.txt", "html", "urls.10K", "kppkn.gtb", "geo.protodata", "fireworks.jpeg"):
         units += blocks_of(corpus(name))[:2]
-    got = emu.compress_units(units, multi=not hybrid, hybrid=hybrid, w64=True, w64_aligned=aligned, grid=2)
+    got = emu.compress_units(units, multi=not hybrid, hybrid=hybrid, w64=True, w64_aligned=aligned, w64_gt=gt, grid=2)
     assert [i for i, (g, u) in enumerate(zip(got, units)) if g != oracle.compress(u)] == []
 
 
