@@ -313,7 +313,10 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": "batched raw block compress+decompress: %d x 64KB synthetic text blocks per GPU (BASELINE configs[1])" % blocks,
                    "blocks_per_gpu": blocks, "block_bytes": BLOCK, "wave_blocks": wave, "ratio": comp_bytes / u_rank,
                    "l2": "inputs larger than L2 (%.1f GiB per GPU per pass)" % (u_rank / 2**30), "parity": parity,
-                   "wall_s_timed_region": wall},
+                   "wall_s_timed_region": wall,
+                   # which build/knobs produced the line (A/B runs of experimental libraries set these)
+                   "lib": os.path.basename(os.environ.get("SNAPB200_LIB", "libsnapb200.so")),
+                   "k1_ng_env": os.environ.get("SNAPB200_K1_NG")},
         "compress_gbs": u_all * args.steps / (ms_cmax / 1e3) / 1e9,
         "decompress_gbs": u_all * args.steps / (ms_dmax / 1e3) / 1e9,
         "roofline": {"bound": "hbm", "kernel": "k1_m7_kernel (K1 compress)", "achieved": k1_achieved, "peak": peak, "unit": "GB/s",
