@@ -157,17 +157,19 @@ int launch_k1(Ctx& c, const sb_batch& b, uint32_t flags, cudaStream_t st, sb_err
         // SNAPB200_K1_NG = extra chains per SM with L2-resident tables (0..7)
         static const int ng_env = getenv("SNAPB200_K1_NG") ? atoi(getenv("SNAPB200_K1_NG")) : K1_DEFAULT_NG;
         const unsigned ng = ng_env < 0 ? 0 : ng_env > K1_MAX_NG ? K1_MAX_NG : (unsigned)ng_env;
-        const unsigned chains = 7 + ng;
+        // small batches spread over the SMs first (one shared-memory-table chain per SM is the fastest a block can
+        // run); only batches with more units than that stack chains on an SM, L2-table chains last
+        unsigned chains = (unsigned)(((uint64_t)b.count + c.sms - 1) / c.sms);
+        if (chains > 7 + ng) chains = 7 + ng;
         unsigned mg = (unsigned)c.sms;
-        if ((uint64_t)mg * chains > b.count) mg = (unsigned)((b.count + chains - 1) / chains);
+        if (mg > b.count) mg = b.count;
         std::lock_guard<std::mutex> k1lk(c.k1_mu);
         CK(cudaStreamWaitEvent(st, c.k1_done, 0));
         CK(cudaMemsetAsync(c.work.p, 0, 4, st));
-        // the template argument only bounds the chain count (register cap, scratch strides): up to 12 chains
-        // (24 warps) the parser keeps its 72 registers, 13-14 chains force it down to 64 (measured 6% slower per chain)
+        // the template argument only bounds the chain count (launch bounds / register cap, scratch strides)
         if (ng > 5) k1_m7_kernel<7><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
         else if (ng > 0) k1_m7_kernel<5><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
-        else k1_m7_kernel<0><<<mg, 7 * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
+        else k1_m7_kernel<0><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
         CK(cudaGetLastError());
         CK(cudaEventRecord(c.k1_done, st));
     } else if (gw) {

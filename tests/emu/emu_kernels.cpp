@@ -34,7 +34,9 @@ int emu_compress_batch(const sb_batch* b, uint32_t flags, unsigned grid) {
         a.rings = rings.data();
         a.gtables = (uint16_t*)(((uintptr_t)gt.data() + 15) & ~(uintptr_t)15);
         a.work = &work;
-        sbemu::launch(grid, (7 + ng) * 64, 7 * sbk::K1_TABLE_BYTES + (7 + ng) * 64, k1_entry, &a);
+        unsigned chains = (flags >> 20) & 15u;                  // 0 = all chains of the layout
+        if (chains == 0 || chains > 7 + ng) chains = 7 + ng;
+        sbemu::launch(grid, chains * 64, 7 * sbk::K1_TABLE_BYTES + (7 + ng) * 64, k1_entry, &a);
         return 0;
     }
     const unsigned np = (flags >> 12) & 7u;

@@ -88,6 +88,13 @@ def test_k1_adversarial_blocks_all_layouts(oracle, mode):
     assert [i for i, (c, u) in enumerate(zip(got, units)) if c != oracle.compress(u)] == []
 
 
+@pytest.mark.parametrize("chains", [1, 2, 8])
+def test_k1_fewer_chains_per_cta(oracle, chains):
+    """Small batches are launched with fewer parser/emitter pairs per CTA (one per SM first)."""
+    units = adversarial_blocks()[:10] + [corpus("alice29.txt")[:65536], b"", b"xy"]
+    assert emu.compress_units(units, hybrid=True, chains=chains, grid=2) == [oracle.compress(u) for u in units]
+
+
 def test_k1_mbarrier_wakeup(oracle):
     """Experimental emitter wake-up through an mbarrier (-DK1_MBAR build) instead of sleep-polling."""
     units = adversarial_blocks()[:16] + [corpus("alice29.txt")[:65536], corpus("kppkn.gtb")[:65536], b"", b"ab"]
