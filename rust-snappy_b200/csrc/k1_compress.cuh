@@ -777,6 +777,7 @@ SB_DEVICE void k1_compress_body(const BatchDesc& b, uint32_t flags) {
 
 }  // namespace sbk
 #include "k1_wide.cuh"   // experimental 64-position step (off unless -DK1_W64)
+#include "k1_exact.cuh"  // second-generation parser: exact windows, pipelined candidate evaluation
 namespace sbk {
 
 // One CTA per SM hosting NC + NG independent (parser, emitter) warp pairs. NC hash tables fill
@@ -791,7 +792,7 @@ namespace sbk {
 //   ctrl[8] = the unit this pair works on
 template <bool GT>
 SB_DEVICE void k1_chain(const BatchDesc& b, uint32_t flags, uint16_t* table, const K1Ring& ring, uint32_t* ctrl,
-                        uint32_t* work, unsigned bar) {
+                        uint32_t* work, unsigned bar, uint32_t* scratch) {
     const unsigned lane = lane_id(), wid = warp_id();
     const bool parser = (wid & 1u) == 0;
     const unsigned pt = (wid & 1u) * 32 + lane;                        // thread index within the pair
@@ -825,7 +826,8 @@ SB_DEVICE void k1_chain(const BatchDesc& b, uint32_t flags, uint16_t* table, con
         bar_sync(bar, 64);
         if (parser) {
             if (n >= 17) {                                                 // (:140-150)
-                if (K1_W64_ON && (!GT || K1_W64_GT_ON)) k1_parse64<GT>(in, n, table, ring, ctrl);
+                if (K1_EXACT_ON && scratch) k1_parse_x<GT>(in, n, table, ring, ctrl, scratch);
+                else if (K1_W64_ON && (!GT || K1_W64_GT_ON)) k1_parse64<GT>(in, n, table, ring, ctrl);
                 else k1_parse_pipelined<1, GT>(in, n, table, ring, ctrl, 0);
             }
             else {                                                         // tiny block: one literal (:140-146)
@@ -842,12 +844,18 @@ SB_DEVICE void k1_chain(const BatchDesc& b, uint32_t flags, uint16_t* table, con
     }
 }
 
-template <int NC, int NG>
+// shared memory of a multi-chain CTA: NC tables, 64 control bytes per chain, and (XS) the second-generation
+// parser's per-chain scratch (byte ring + info ring)
+constexpr size_t k1_multi_smem(int NC, int NG, bool XS) {
+    return (size_t)NC * K1_TABLE_BYTES + (size_t)(NC + NG) * 64 + (XS ? (size_t)(NC + NG) * K1X_SCRATCH_BYTES : 0);
+}
+template <int NC, int NG, bool XS = false>
 SB_DEVICE void k1_compress_body_multi(const BatchDesc& b, uint32_t flags, uint64_t* ring_scratch, uint16_t* gtables,
                                       uint32_t* work) {
     uint8_t* sm = smem();
     const unsigned c = warp_id() >> 1;                                 // chain within the CTA
     uint32_t* ctrl = (uint32_t*)(sm + (size_t)NC * K1_TABLE_BYTES + c * 64);
+    uint32_t* scratch = XS ? (uint32_t*)(sm + (size_t)NC * K1_TABLE_BYTES + (size_t)(NC + NG) * 64 + (size_t)c * K1X_SCRATCH_BYTES) : nullptr;
     K1Ring ring;
     ring.size = K1_RING_GW;
     ring.ev = ring_scratch + ((size_t)block_idx() * (NC + NG) + c) * K1_RING_GW;
@@ -857,8 +865,8 @@ SB_DEVICE void k1_compress_body_multi(const BatchDesc& b, uint32_t flags, uint64
 #elif defined(SB_EMU)
     ring.mbar = (flags & 8u) != 0;
 #endif
-    if (NG == 0 || c < NC) k1_chain<false>(b, flags, (uint16_t*)(sm + (size_t)c * K1_TABLE_BYTES), ring, ctrl, work, 1 + c);
-    else k1_chain<true>(b, flags, gtables + ((size_t)block_idx() * NG + (c - NC)) * (K1_TABLE_BYTES / 2), ring, ctrl, work, 1 + c);
+    if (NG == 0 || c < NC) k1_chain<false>(b, flags, (uint16_t*)(sm + (size_t)c * K1_TABLE_BYTES), ring, ctrl, work, 1 + c, scratch);
+    else k1_chain<true>(b, flags, gtables + ((size_t)block_idx() * NG + (c - NC)) * (K1_TABLE_BYTES / 2), ring, ctrl, work, 1 + c, scratch);
 }
 
 }  // namespace sbk

@@ -36,6 +36,13 @@ __global__ void __launch_bounds__((7 + NG) * 64, 1)
 k1_m7_kernel(sb_batch b, uint32_t flags, uint64_t* rings, uint16_t* gtables, uint32_t* work) {
     sbk::k1_compress_body_multi<7, NG>(b, flags, rings, gtables, work);
 }
+// second-generation parser (k1_exact.cuh): 6 shared-memory tables + per-chain byte/info rings, NG chains with L2 tables
+template <int NG>
+__global__ void __launch_bounds__((6 + NG) * 64, 1)
+k1_x_kernel(sb_batch b, uint32_t flags, uint64_t* rings, uint16_t* gtables, uint32_t* work) {
+    sbk::k1_compress_body_multi<6, NG, true>(b, flags, rings, gtables, work);
+}
+const int K1X_MAX_NG = 10;
 const int K1_MAX_NG = 7;
 const size_t K1_M7_SMEM = 7 * sbk::K1_TABLE_BYTES + (7 + K1_MAX_NG) * 64;
 __global__ void __launch_bounds__(128) k2_decompress_kernel(sb_batch b) { sbk::k2_decompress_body(b); }
@@ -118,8 +125,13 @@ int get_ctx(Ctx** out, sb_error* err) {
         CK(cudaFuncSetAttribute(k1_m7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
         CK(cudaFuncSetAttribute(k1_m7_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
         CK(cudaFuncSetAttribute(k1_m7_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
-        CK(c.rings.need((size_t)c.sms * (7 + K1_MAX_NG) * sbk::K1_RING_GW * 8));
-        CK(c.gtables.need((size_t)c.sms * K1_MAX_NG * sbk::K1_TABLE_BYTES));
+        CK(cudaFuncSetAttribute(k1_x_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::k1_multi_smem(6, 0, true)));
+        CK(cudaFuncSetAttribute(k1_x_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::k1_multi_smem(6, 4, true)));
+        CK(cudaFuncSetAttribute(k1_x_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::k1_multi_smem(6, 6, true)));
+        CK(cudaFuncSetAttribute(k1_x_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::k1_multi_smem(6, 8, true)));
+        CK(cudaFuncSetAttribute(k1_x_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::k1_multi_smem(6, 10, true)));
+        CK(c.rings.need((size_t)c.sms * 16 * sbk::K1_RING_GW * 8));
+        CK(c.gtables.need((size_t)c.sms * K1X_MAX_NG * sbk::K1_TABLE_BYTES));
         CK(c.work.need(256));
         CK(cudaEventCreateWithFlags(&c.k1_done, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&c.s_compute, cudaStreamNonBlocking));
@@ -153,7 +165,28 @@ int launch_k1(Ctx& c, const sb_batch& b, uint32_t flags, cudaStream_t st, sb_err
     if (grid > b.count) grid = b.count;
     const size_t sm = gw ? sbk::K1_SMEM_BYTES_GW : sbk::K1_SMEM_BYTES;
     static const int multi = getenv("SNAPB200_K1_MULTI") ? atoi(getenv("SNAPB200_K1_MULTI")) : K1_DEFAULT_MULTI;
-    if (multi) {
+    static const int xmode = getenv("SNAPB200_K1_X") ? atoi(getenv("SNAPB200_K1_X")) : 1;
+    if (xmode) {
+        // SNAPB200_K1_NG = chains per SM with L2-resident tables next to the 6 shared-memory ones (0..10)
+        static const int ng_env = getenv("SNAPB200_K1_NG") ? atoi(getenv("SNAPB200_K1_NG")) : 6;
+        const unsigned ng = ng_env < 0 ? 0 : ng_env > K1X_MAX_NG ? K1X_MAX_NG : (unsigned)ng_env;
+        unsigned chains = (unsigned)(((uint64_t)b.count + c.sms - 1) / c.sms);
+        if (chains > 6 + ng) chains = 6 + ng;
+        unsigned mg = (unsigned)c.sms;
+        if (mg > b.count) mg = b.count;
+        std::lock_guard<std::mutex> k1lk(c.k1_mu);
+        CK(cudaStreamWaitEvent(st, c.k1_done, 0));
+        CK(cudaMemsetAsync(c.work.p, 0, 4, st));
+        uint64_t* rg = c.rings.as<uint64_t>(); uint16_t* gt = c.gtables.as<uint16_t>(); uint32_t* wk = c.work.as<uint32_t>();
+        // the template argument bounds the chain count (launch bounds / register cap, scratch strides)
+        if (ng > 8) k1_x_kernel<10><<<mg, chains * 64, sbk::k1_multi_smem(6, 10, true), st>>>(b, flags, rg, gt, wk);
+        else if (ng > 6) k1_x_kernel<8><<<mg, chains * 64, sbk::k1_multi_smem(6, 8, true), st>>>(b, flags, rg, gt, wk);
+        else if (ng > 4) k1_x_kernel<6><<<mg, chains * 64, sbk::k1_multi_smem(6, 6, true), st>>>(b, flags, rg, gt, wk);
+        else if (ng > 0) k1_x_kernel<4><<<mg, chains * 64, sbk::k1_multi_smem(6, 4, true), st>>>(b, flags, rg, gt, wk);
+        else k1_x_kernel<0><<<mg, chains * 64, sbk::k1_multi_smem(6, 0, true), st>>>(b, flags, rg, gt, wk);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c.k1_done, st));
+    } else if (multi) {
         // SNAPB200_K1_NG = extra chains per SM with L2-resident tables (0..7)
         static const int ng_env = getenv("SNAPB200_K1_NG") ? atoi(getenv("SNAPB200_K1_NG")) : K1_DEFAULT_NG;
         const unsigned ng = ng_env < 0 ? 0 : ng_env > K1_MAX_NG ? K1_MAX_NG : (unsigned)ng_env;

@@ -54,7 +54,7 @@ def _pack(chunks, slack=64):
     return buf, offs
 
 
-def compress_units(units, with_header=True, grid=1, global_window=False, parsers=1, multi=False, hybrid=False, mbar=False, gt_spec=False, w64=False, w64_aligned=False, unaligned=False, w64_gt=False, chains=0):
+def compress_units(units, with_header=True, grid=1, global_window=False, parsers=1, multi=False, hybrid=False, mbar=False, gt_spec=False, w64=False, w64_aligned=False, unaligned=False, w64_gt=False, chains=0, exact=False):
     """Run the K1 kernel body under the emulator over independent units (<=64KB each)."""
     inbuf, inoffs = _pack(units, slack=3)
     stride = 76544
@@ -70,7 +70,7 @@ def compress_units(units, with_header=True, grid=1, global_window=False, parsers
     b.out_cap_uniform = stride
     b.out_lens = out_lens.ctypes.data
     b.count = len(units)
-    lib().emu_compress_batch(C.byref(b), (1 if with_header else 0) | (0x100 if global_window else 0) | (parsers << 12) | (0x200 if multi else 0) | (0x400 if hybrid else 0) | (0x800 if mbar else 0) | (0x8000 if gt_spec else 0) | (0x10000 if w64 else 0) | (0x20000 if w64_aligned else 0) | (0x40000 if unaligned else 0) | (0x80000 if w64_gt else 0) | (chains << 20), grid)
+    lib().emu_compress_batch(C.byref(b), (1 if with_header else 0) | (0x100 if global_window else 0) | (parsers << 12) | (0x200 if multi else 0) | (0x400 if hybrid else 0) | (0x800 if mbar else 0) | (0x8000 if gt_spec else 0) | (0x10000 if w64 else 0) | (0x20000 if w64_aligned else 0) | (0x40000 if unaligned else 0) | (0x80000 if w64_gt else 0) | (chains << 20) | (0x1000000 if exact else 0), grid)
     return [bytes(out[i * stride:i * stride + int(out_lens[i])]) for i in range(len(units))]
 
 

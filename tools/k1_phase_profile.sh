@@ -28,6 +28,15 @@ L.sb_debug_k1_profile(out, 1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); L.sb_compress_batch_device(C.byref(b), st, C.byref(err)); e1.record(); torch.cuda.synchronize()
 L.sb_debug_k1_profile(out, 0)
+if os.environ.get("SNAPB200_K1_X", "1") != "0":
+    names = ["byte ring upkeep", "chunk pipeline (complete+issue)", "event ring space", "own bytes/hash/slot/info", "moved slots",
+             "match.any + dynamic lanes", "walk", "commit", "exit state/publish/loop", "serial path", "block end", "windows"]
+    wins = out[11]
+    tot = sum(out[i] for i in range(11))
+    print("kernel %.2f ms, %.2f GB/s; windows %d (%.1f bytes each); parser cycles per window: %.0f" % (e0.elapsed_time(e1), n * BLOCK / e0.elapsed_time(e1) / 1e6, wins, n * BLOCK / max(1, wins), tot / max(1, wins)))
+    for i in range(11):
+        print("  [%2d] %-34s %6.1f%%  %7.0f cyc/window" % (i, names[i], 100.0 * out[i] / tot, out[i] / max(1, wins)))
+    sys.exit(0)
 names = ["loop top/prefetch", "probe (hash,table,cand,compare)", "pointer doubling", "entry->taken copies", "interiors/inserted mask",
          "commit+verify(+clash)", "event ring", "exit state/copy-end insert", "(pre-serial)", "serial path", "block end", ""]
 tot = sum(out[i] for i in range(11))
