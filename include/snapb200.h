@@ -50,6 +50,14 @@ typedef struct sb_error {
     uint64_t a, b, c;
 } sb_error;
 
+/* Outcome of a stream-ordered frame call, written to device memory by the last kernel of the call. */
+typedef struct sb_frame_result {
+    sb_error status;                 /* SB_OK or the first error in stream order                  */
+    uint64_t bytes;                  /* encode: stream length; decode: bytes produced before the error */
+    uint32_t nchunks;                /* data chunks in the stream                                  */
+    uint32_t _pad;
+} sb_frame_result;
+
 /* ---- scalar API: host pointers, mirrors snap::raw ------------------------ */
 
 /* snap::raw::max_compress_len  (src/compress.rs:42-53). Pure arithmetic. */
@@ -81,6 +89,13 @@ int sb_compress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, cons
 int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, const uint32_t* in_lens,
                              uint8_t* out_base, const uint64_t* out_offs, const uint32_t* out_caps,
                              uint32_t* out_lens, sb_error* statuses, size_t count, sb_error* err);
+/* Same compress, but the LIBRARY lays the streams out back to back in out_base[0 .. out_cap) and reports where:
+ * out_offs receives count+1 entries (out_offs[count] = total bytes). A caller cannot know compressed sizes in
+ * advance, so this is the form whose drain is one D2H copy per wave; sb_max_compress_len(len) summed over the
+ * units is always enough capacity. Units are one block each (in_lens[i] <= 65536, else TooBig). */
+int sb_compress_batch_host_packed(const uint8_t* in_base, const uint64_t* in_offs, const uint32_t* in_lens,
+                                  uint8_t* out_base, uint64_t out_cap, uint64_t* out_offs, uint32_t* out_lens,
+                                  size_t count, sb_error* err);
 
 /* ---- batched device API: device pointers, stream ordered ------------------
  * The kernels' native interface (and what bench.py's `value` times). All
@@ -97,11 +112,16 @@ typedef struct sb_batch {
     uint32_t count;
 } sb_batch;
 
-/* Each unit (<= 4 GiB - 1) becomes one raw stream exactly as Encoder::compress
- * would produce it. Units of <= 65536 bytes are one block per parser/emitter
- * warp pair (12 pairs per SM). Compress launches share a per-device scratch
- * (event rings, L2-resident hash tables, work counter): launches issued on
- * different streams of one device are ordered after each other on the device. */
+/* Each unit is ONE BLOCK: at most 65536 bytes, and its output slot must hold
+ * sb_max_compress_len(len) bytes; the unit becomes one raw stream exactly as
+ * Encoder::compress would produce it (one parser/emitter warp pair per unit, 12
+ * pairs per SM). A unit that breaks either limit is skipped: out_lens[i] = 0 and,
+ * when `statuses` is given, TooBig{given,max=65536} / BufferTooSmall{given,min}
+ * (src/compress.rs:104-117); uniform lengths/caps are also checked on the host.
+ * Larger inputs go through sb_compress / sb_frame_encode_device, which cut them
+ * into blocks. Compress launches share a per-device scratch (event rings,
+ * L2-resident hash tables, work counter): launches issued on different streams
+ * of one device are ordered after each other on the device. */
 int sb_compress_batch_device(const sb_batch* batch, void* stream, sb_error* err);
 /* Each unit is one raw stream; statuses[i] carries the reference's error. */
 int sb_decompress_batch_device(const sb_batch* batch, void* stream, sb_error* err);
@@ -125,9 +145,55 @@ int sb_frame_decode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_
 
 /* Device-resident frame encode of n bytes at d_in (device) into d_out (device,
  * cap >= sb_frame_max_len(n)); *out_n (host) = stream length. include_ident=0
- * omits the 10-byte stream identifier (ranks > 0 of a sharded stream). */
+ * omits the 10-byte stream identifier (ranks > 0 of a sharded stream).
+ * Convenience form: pooled scratch, waits for the result. */
 int sb_frame_encode_device(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap,
                            int include_ident, uint64_t* out_n, void* stream, sb_error* err);
+
+/* ---- stream-ordered frame calls with caller-provided scratch ---------------
+ * No allocation, no host synchronisation (n > 0): every kernel of the call is
+ * enqueued on `stream` and the outcome is written to *d_result (device memory).
+ *   scratch: device memory of at least sb_frame_{encode,decode}_scratch_bytes(..).
+ * Encode (src/write.rs:165-192 + src/frame.rs:62-104): K1 compresses every chunk
+ * and leaves its masked CRC-32C beside it, a two-level scan places the chunks,
+ * one gather writes headers + bodies. d_chunk_offs (optional, device, nchunks+1
+ * entries) receives the offset of every chunk header in d_out and the total --
+ * the chunk index sb_frame_decode_device_ws accepts. */
+uint64_t sb_frame_encode_scratch_bytes(uint64_t n);
+int sb_frame_encode_device_ws(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap, int include_ident,
+                              uint64_t* d_chunk_offs, sb_frame_result* d_result, void* scratch, uint64_t scratch_bytes,
+                              void* stream, sb_error* err);
+/* Decode (read::FrameDecoder, src/read.rs:104-239) of a frame stream in device
+ * memory. With d_chunk_offs/nchunks (the encoder's index; d_chunk_offs[nchunks]
+ * = n) the chunk headers are parsed in parallel; without it (or when the index
+ * does not describe a clean run of data chunks) one thread walks the headers in
+ * stream order exactly like the reference's reader. Then one warp per chunk:
+ * raw decode (K2) or copy, masked CRC-32C of the produced bytes against the
+ * header. d_result: first error in stream order + bytes produced before it.
+ *   flags bit0: no stream identifier expected (a rank's fragment of a sharded stream)
+ *   max_chunks: capacity of the chunk table carved from scratch (SB_E_INVALID{a=max_chunks,b=1} if exceeded) */
+uint64_t sb_frame_decode_scratch_bytes(uint32_t max_chunks);
+int sb_frame_decode_device_ws(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap,
+                              const uint64_t* d_chunk_offs, uint32_t nchunks, uint32_t flags,
+                              sb_frame_result* d_result, void* scratch, uint64_t scratch_bytes, uint32_t max_chunks,
+                              void* stream, sb_error* err);
+/* Convenience form: pooled scratch, waits and returns the result on the host. */
+int sb_frame_decode_device(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap,
+                           const uint64_t* d_chunk_offs, uint32_t nchunks, uint32_t flags,
+                           sb_frame_result* result, void* stream, sb_error* err);
+
+/* ---- resources -------------------------------------------------------------
+ * The host entry points keep grow-only per-device pools (device staging, pinned
+ * descriptors, streams, events): the first calls size them, the steady state
+ * allocates nothing. sb_reserve sizes them ahead of time for waves of up to
+ * wave_units units / wave_in_bytes input / wave_out_bytes output;
+ * sb_alloc_count() = allocations + event/stream creations since load (a caller
+ * can assert it stays flat). First use of a device is thread safe. */
+int sb_reserve(size_t wave_units, size_t wave_in_bytes, size_t wave_out_bytes, sb_error* err);
+uint64_t sb_alloc_count(void);
+/* Pin the calling thread to the CPUs of the NUMA node of `device` (so that pinned staging it allocates afterwards
+ * and its copies stay on the near socket). Returns the node, or -1 when the topology is not exposed. */
+int sb_bind_host_thread_to_device_numa(int device);
 
 /* ---- libsnappy-compatible C API ------------------------------------------
  * The four functions the reference's `snappy-cpp` crate binds

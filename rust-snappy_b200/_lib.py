@@ -16,6 +16,10 @@ class SbError(C.Structure):
                 ("a", C.c_uint64), ("b", C.c_uint64), ("c", C.c_uint64)]
 
 
+class SbFrameResult(C.Structure):
+    _fields_ = [("status", SbError), ("bytes", C.c_uint64), ("nchunks", C.c_uint32), ("_pad", C.c_uint32)]
+
+
 class SbBatch(C.Structure):
     _fields_ = [
         ("in_ptrs", C.c_void_p), ("in_base", C.c_void_p), ("in_stride", C.c_uint64),
@@ -29,9 +33,12 @@ class SbBatch(C.Structure):
 # every symbol include/snapb200.h declares
 SYMBOLS = [
     "sb_max_compress_len", "sb_compress", "sb_decompress_len", "sb_decompress", "sb_crc32c_masked",
-    "sb_compress_batch_host", "sb_decompress_batch_host",
+    "sb_compress_batch_host", "sb_decompress_batch_host", "sb_compress_batch_host_packed",
     "sb_compress_batch_device", "sb_decompress_batch_device", "sb_crc32c_masked_batch_device",
     "sb_frame_max_len", "sb_frame_encode", "sb_frame_encode_ex", "sb_frame_decode", "sb_frame_encode_device",
+    "sb_frame_encode_scratch_bytes", "sb_frame_encode_device_ws", "sb_frame_decode_scratch_bytes",
+    "sb_frame_decode_device_ws", "sb_frame_decode_device", "sb_reserve", "sb_alloc_count",
+    "sb_bind_host_thread_to_device_numa",
     "sb_launch_count", "sb_generate_blocks_device", "sb_version",
     "snappy_compress", "snappy_uncompress", "snappy_max_compressed_length", "snappy_uncompressed_length",
 ]
@@ -69,6 +76,19 @@ def lib():
     L.sb_frame_encode_ex.argtypes = [vp, sz, vp, sz, szp, C.c_int, ep]
     L.sb_frame_decode.argtypes = [vp, sz, vp, sz, szp, ep]
     L.sb_frame_encode_device.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.c_int, u64p, vp, ep]
+    L.sb_compress_batch_host_packed.argtypes = [vp, vp, vp, vp, C.c_uint64, vp, vp, sz, ep]
+    L.sb_frame_encode_scratch_bytes.restype = C.c_uint64
+    L.sb_frame_encode_scratch_bytes.argtypes = [C.c_uint64]
+    L.sb_frame_decode_scratch_bytes.restype = C.c_uint64
+    L.sb_frame_decode_scratch_bytes.argtypes = [C.c_uint32]
+    L.sb_frame_encode_device_ws.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.c_int, vp, vp, vp, C.c_uint64, vp, ep]
+    L.sb_frame_decode_device_ws.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64,
+                                            C.c_uint32, vp, ep]
+    L.sb_frame_decode_device.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint32, C.c_uint32,
+                                         C.POINTER(SbFrameResult), vp, ep]
+    L.sb_reserve.argtypes = [sz, sz, sz, ep]
+    L.sb_alloc_count.restype = C.c_uint64
+    L.sb_bind_host_thread_to_device_numa.argtypes = [C.c_int]
     L.sb_generate_blocks_device.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.c_uint64,
                                             C.c_uint64, C.c_uint64, vp, ep]
     L.snappy_max_compressed_length.restype = sz

@@ -1,5 +1,4 @@
-// k1_compress.cuh -- K1: batched raw Snappy block encode, one <=64KB block per
-// CTA, bit-exact with the reference encoder.
+// k1_compress.cuh -- K1: batched raw Snappy block encode, bit-exact with the reference encoder.
 //
 // Replaces reference src/compress.rs:195-317 (Block::compress), :323-369
 // (emit_copy/emit_copy2), :378-412 (extend_match), :417-426 (done), :433-474
@@ -8,8 +7,10 @@
 //
 // The greedy parse is a serial dependency chain (every table insert depends on
 // every earlier match decision), so bit-exactness forbids a "better" parallel
-// match finder. The CTA is two warps around one block held in shared memory
-// (64KB window + 16K-entry u16 hash table):
+// match finder. One CTA per SM hosts several independent chains; a chain is a
+// pair of warps working on one <=64KB block that is read in place from global
+// memory / L2, with its 16K-entry u16 hash table in shared memory (7 chains) or in
+// an L2-resident global scratch (the others):
 //
 //  * PARSER warp. Looks at 32 consecutive positions at once. Every lane hashes
 //    its position, reads the table as of the window start, fetches its
@@ -18,17 +19,23 @@
 //    (rematch hit at the copy end, else the first later hit of the scan), pointer
 //    doubling from the window's entry state yields the copies the serial encoder
 //    takes, and the inserted positions are "everything except copy interiors".
-//    The inserts are committed, re-read, and if two inserted lanes collided on a
-//    slot (the one case where a lane's candidate would have come from inside the
-//    window) the window is undone and replayed by the serial path below.
+//    The inserts are committed; if two inserted lanes collided on a slot, the
+//    window is accepted up to the first lane whose candidate should have come from
+//    inside the window and restarts there.
 //  * serial path: the reference's control flow executed by the warp (scan probes
 //    32 at a time with match.any conflict resolution, 128-byte match extension).
-//    Used for replays, for scan runs past 32 probes (stride > 1) and the block tail.
+//    Used for scan runs past 32 probes (stride > 1) and the block tail.
 //  * EMITTER warp. Consumes the parser's (position, length, offset) copy events
-//    from a shared-memory ring, 32 at a time: literal/copy tag sizes, a warp scan
-//    for output offsets, tags and literal bytes written straight to HBM.
+//    from a ring, 32 at a time: literal/copy tag sizes, a warp scan for output
+//    offsets, tags and literal bytes written straight to HBM (evict-first).
+//
+// Measured and rejected in round 2 (profiles/r2_k1_variants_ab.txt): 64-position steps, unaligned windows,
+// speculative slot reads for the L2-table chains, an mbarrier wake-up for the emitter, and a second-generation
+// parser with exact windows and pipelined candidate evaluation. The one-pair-per-CTA layouts of round 1
+// (shared-memory window, pipelined parser warps) are gone as well; their numbers are in DESIGN.md.
 #pragma once
 #include "common.cuh"
+#include "k3_crc32c.cuh"
 
 #if defined(K1_PROFILE) && defined(__CUDACC__)
 // Optional phase timers for kernel archaeology (tools/k1_phase_profile.sh builds a separate
@@ -49,11 +56,8 @@ __device__ unsigned long long g_k1_prof[16];
 
 namespace sbk {
 
-static const uint32_t K1_WIN_BYTES = 65536 + 64;             // window + slack for over-reads
 static const uint32_t K1_TABLE_BYTES = 32768;                // 16K-entry u16 table
-static const uint32_t K1_RING = 1024;                        // copy events in flight (shared-memory window variant)
-static const uint32_t K1_RING_GW = 256;                      // ... global-window variant (6 CTAs/SM)
-static const uint32_t K1_SMEM_BYTES = K1_WIN_BYTES + K1_TABLE_BYTES + K1_RING * 8 + 64;
+static const uint32_t K1_RING_GW = 256;                      // copy events in flight per chain (global scratch, L2 resident)
 
 // 4 bytes at win+p through two aligned word loads. `win` may be a shared-memory window
 // (4-byte aligned) or the unit's input in global memory (any alignment): the loads are
@@ -74,15 +78,8 @@ SB_DEVICE uint32_t k1_rd32_end(const uint8_t* win, uint32_t p, uint32_t n) {
 // ---------------------------------------------------------------- event ring
 struct K1Ring {
     uint64_t* ev;        // `size` entries (power of two)
-    uint32_t* ctrl;      // [0]=head (produced), [1]=tail (consumed), [9]=publish count, [10..11]=mbarrier (when `mbar`)
+    uint32_t* ctrl;      // [0]=head (produced), [1]=tail (consumed), [6..7]=producer counters between units, [8]=unit
     uint32_t size;
-    // emitter blocks on the mbarrier at ctrl[10] instead of sleep-polling ctrl[0]: experimental, compile with -DK1_MBAR
-    // (tools/build_variant.sh mbar -DK1_MBAR, then SNAPB200_LIB=.../libsnapb200_mbar.so); not measured on hardware yet
-#if defined(K1_MBAR) || defined(SB_EMU)
-    bool mbar = false;
-#else
-    static constexpr bool mbar = false;
-#endif
 };
 SB_DEVICE uint64_t k1_event(uint32_t pos, uint32_t len, uint32_t off) {
     return (uint64_t)pos | ((uint64_t)len << 17) | ((uint64_t)off << 34);
@@ -102,13 +99,7 @@ SB_DEVICE void k1_publish(const K1Ring& r, K1Prod& pr) {
     if (pr.published == pr.head) return;
     threadfence_block();
     syncwarp();
-    if (lane_id() == 0) {
-        st_volatile(&r.ctrl[0], pr.head);
-        if (r.mbar) {                                      // head first, then the publish count, then the wake-up
-            st_volatile(&r.ctrl[9], ld_volatile(&r.ctrl[9]) + 1u);
-            mbar_arrive((uint64_t*)&r.ctrl[10]);
-        }
-    }
+    if (lane_id() == 0) st_volatile(&r.ctrl[0], pr.head);
     pr.published = pr.head;
 }
 SB_DEVICE void k1_wait_space(const K1Ring& r, K1Prod& pr, uint32_t need) {
@@ -154,31 +145,6 @@ struct K1State {
 };
 
 #define K1_HASH(x) (((uint32_t)(x) * 0x1E35A7BDu) >> shift)
-// Experimental (-DK1_GT_SPEC, not measured on hardware yet): chains whose table lives in L2 read the NEXT window's
-// slots before the current window commits, fetch candidates for those values and re-read the slots afterwards, so the
-// two L2 round trips of a probe overlap; a slot that moved in between costs one more candidate fetch.
-// Experimental (-DK1_UNALIGNED, not measured on hardware yet): the single-parser loop starts each 32-position window
-// where the parse stands instead of on a 32-byte boundary (tools/sim_window_width.py: 33.5 bytes per step on text
-// against 30.3); the prefetch then guesses that the next window starts at w + 32.
-#if defined(SB_EMU)
-static bool g_k1_unaligned = false;                    // set by the test harness
-#define K1_UNALIGNED_ON g_k1_unaligned
-#elif defined(K1_UNALIGNED)
-#define K1_UNALIGNED_ON true
-#else
-#define K1_UNALIGNED_ON false
-#endif
-#if defined(SB_EMU)
-static bool g_k1_gt_spec = false;                      // set by the test harness
-static unsigned long g_k1_spec_stat[2] = {0, 0};       // speculated windows, of which had to fetch candidates again
-static unsigned long g_k1_w32_stat[3] = {0, 0, 0};     // fast steps, bytes they resolved, windows replayed serially
-#define K1_GT_SPEC_ON g_k1_gt_spec
-#elif defined(K1_GT_SPEC)
-#define K1_GT_SPEC_ON true
-#else
-#define K1_GT_SPEC_ON false
-#endif
-
 // after a copy ends at e: `if s >= s_limit return` else insert e-1 (:275-295)
 SB_DEVICE void k1_preinsert(const uint8_t* win, uint16_t* table, unsigned shift, uint32_t s_limit, uint32_t e) {
     if (e < s_limit) {
@@ -299,9 +265,7 @@ SB_DEVICE uint32_t k1_double(uint32_t E, bool eq, uint32_t L) {
     return M;
 }
 
-template <bool SPEC = false>
-SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w, const K1Seq* seq K1_PROF_ARGS,
-                        uint32_t spec_c = 0, uint32_t spec_i0 = 0) {
+SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shift, uint32_t w, const K1Seq* seq K1_PROF_ARGS) {
     const uint32_t p = w + lane_id();
     K1Pre r;
     const uintptr_t aa = (uintptr_t)(win + p);
@@ -311,31 +275,11 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
     else { const K1Seq q = k1_fetch_seq(win, w); a0 = q.a0; a1 = q.a1; a2 = q.a2; a3 = q.a3; a4 = q.a4; }
     const uint32_t cur = funnel_r(a0, a1, ash);
     r.h = K1_HASH(cur);
-    uint32_t b0, b1, b2, b3, b4;
-    unsigned bsh;
-    if (SPEC) {
-        // candidate words for the slot value seen before the previous commit, in flight together with the re-read
-        uintptr_t ba = (uintptr_t)(win + spec_c);
-        const uint32_t* bw = (const uint32_t*)(ba & ~(uintptr_t)3);
-        b0 = bw[0]; b1 = bw[1]; b2 = bw[2]; b3 = bw[3]; b4 = bw[4];
-        r.c = table[r.h];
-        const bool moved = any(lane_id() >= spec_i0 && r.c != spec_c);   // lanes before the entry position do not matter
-#if defined(SB_EMU)
-        if (lane_id() == 0) { g_k1_spec_stat[0]++; g_k1_spec_stat[1] += moved ? 1 : 0; }
-#endif
-        if (moved) {                                             // a slot moved: fetch again from the current values
-            ba = (uintptr_t)(win + r.c);
-            bw = (const uint32_t*)(ba & ~(uintptr_t)3);
-            b0 = bw[0]; b1 = bw[1]; b2 = bw[2]; b3 = bw[3]; b4 = bw[4];
-        }
-        bsh = (unsigned)((uintptr_t)(win + r.c) & 3u) * 8;
-    } else {
-        r.c = table[r.h];
-        const uintptr_t ba = (uintptr_t)(win + r.c);
-        const uint32_t* bw = (const uint32_t*)(ba & ~(uintptr_t)3);
-        bsh = (unsigned)(ba & 3u) * 8;
-        b0 = bw[0]; b1 = bw[1]; b2 = bw[2]; b3 = bw[3]; b4 = bw[4];
-    }
+    r.c = table[r.h];
+    const uintptr_t ba = (uintptr_t)(win + r.c);
+    const uint32_t* bw = (const uint32_t*)(ba & ~(uintptr_t)3);
+    const unsigned bsh = (unsigned)(ba & 3u) * 8;
+    const uint32_t b0 = bw[0], b1 = bw[1], b2 = bw[2], b3 = bw[3], b4 = bw[4];
     r.eq = cur == funnel_r(b0, b1, bsh);
     // match length, branch-free: bytes 4..15 of both sides, first differing byte wins
     {
@@ -362,10 +306,9 @@ SB_DEVICE K1Pre k1_eval(const uint8_t* win, const uint16_t* table, unsigned shif
 // full L2 round trip there, so slot clashes are found by comparing hashes across lanes.
 template <bool GT>
 SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
-                         K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre& pre, const K1Seq* nxt K1_PROF_ARGS,
-                         uint32_t wbase = 0xFFFFFFFFu) {
+                         K1State& st, const K1Ring& ring, K1Prod& head, const K1Pre& pre, const K1Seq* nxt K1_PROF_ARGS) {
     const unsigned lane = lane_id();
-    const uint32_t w = wbase != 0xFFFFFFFFu ? wbase : (st.s & ~31u), i0 = st.s - w, p = w + lane;
+    const uint32_t w = st.s & ~31u, i0 = st.s - w, p = w + lane;
     const uint32_t h = pre.h, c = pre.c, E = pre.E;
     const bool eq = pre.eq;
     uint32_t L = pre.L;
@@ -489,107 +432,38 @@ SB_DEVICE bool k1_finish(const uint8_t* win, uint32_t n, uint16_t* table, unsign
     return true;
 }
 
-SB_DEVICE bool k1_window(const uint8_t* win, uint32_t n, uint16_t* table, unsigned shift, uint32_t s_limit,
-                         K1State& st, const K1Ring& ring, K1Prod& head) {
-    K1_PROF_DECL
-    const K1Pre pre = k1_eval(win, table, shift, st.s & ~31u, nullptr K1_PROF_PASS);
-    return k1_finish<false>(win, n, table, shift, s_limit, st, ring, head, pre, nullptr K1_PROF_PASS);
-}
-
-// Parser warps: block visible through `win`, n >= 17. NP warps take turns over the
-// 32-position windows (window index = position / 32). While it waits for the token a
-// warp probes its next window against the table as it is NOW (a few inserts stale);
-// when the token arrives it re-reads the table slots and only re-probes if a slot it
-// depends on moved, so everything except walk+commit is off the critical path.
-// The token travels round-robin over named barriers (bar.arrive -> bar.sync): hardware
-// wake-up, and the barrier orders the shared-memory state/table writes.
-//   ctrl[2] = turn (index of the window to commit next, K1_DONE when the block is finished)
-//   ctrl[3..5] = parse state (s, skip, rematch)   ctrl[6..7] = ring producer (head, published)
-static const uint32_t K1_DONE = 0xFFFFFFFFu;
-
-template <int NP, bool GT = false>
-SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* table, const K1Ring& ring,
-                                  uint32_t* ctrl, unsigned k) {
+// Parser warp: block visible through `win` (global memory), n >= 17. One 32-position window per step;
+// the sequential words of the next window are requested before the current one is probed.
+//   ctrl[6..7] = ring producer counters (head, published), carried from unit to unit
+template <bool GT>
+SB_DEVICE void k1_parse(const uint8_t* win, uint32_t n, uint16_t* table, const K1Ring& ring, uint32_t* ctrl) {
     const unsigned lane = lane_id();
     unsigned shift = 24;
     uint32_t tsize = 256;
     while (tsize < 16384 && tsize < n) { shift--; tsize *= 2; }   // src/compress.rs:491-497
     const uint32_t s_limit = n - 15;
     K1Prod prod;
-    prod.head = 0; prod.published = 0; prod.tail_seen = 0;
-    const unsigned bar_mine = 1 + k, bar_next = 1 + (k + 1) % NP;
+    prod.head = ld_volatile(&ctrl[6]); prod.published = ld_volatile(&ctrl[7]); prod.tail_seen = 0;
     K1Seq seq;
-    seq.a0 = seq.a1 = seq.a2 = seq.a3 = 0; seq.w = 0xFFFFFFFFu;
+    seq.a0 = seq.a1 = seq.a2 = seq.a3 = seq.a4 = 0; seq.w = 0xFFFFFFFFu;
     K1_PROF_DECL
-    uint32_t my = k;
-    K1State lst;                                                   // NP == 1: parse state kept in registers
-    lst.s = 1; lst.skip = 32; lst.rematch = false;
-    uint32_t spec_c = 0, spec_w = 0xFFFFFFFFu;                     // speculative slot values of the next window (K1_GT_SPEC)
-    bool first = (k == 0);                                         // warp 0 starts with the token
+    K1State st;
+    st.s = 1; st.skip = 32; st.rematch = false;
     for (;;) {
-        // probe ahead (stale table) while the token is elsewhere
-        bool have = false;
-        K1Pre pre;
-        pre.h = pre.c = pre.L = pre.E = pre.M = pre.longs = 0; pre.eq = false;
-        uint32_t w = my * 32;
-        if (NP > 1 && !first && w + 36 < s_limit) {
-            // my window after this one: start its sequential-word loads now, they are back by the time I probe it
-            K1Seq nx = seq;
-            if (w + NP * 32 + 100 < n) nx = k1_fetch_seq(win, w + NP * 32);
-            pre = k1_eval(win, table, shift, w, &seq K1_PROF_PASS);
-            seq = nx;
-            have = true;
-        }
-        if (NP > 1 && !first) bar_sync(bar_mine, 64);              // token arrives
-        first = false;
-        K1State st;
-        if (NP == 1) {
-            // single parser: state lives in registers, only the producer counters persist across units
-            if (my == 0) { lst.s = 1; lst.skip = 32; lst.rematch = false; prod.head = ld_volatile(&ctrl[6]); prod.published = ld_volatile(&ctrl[7]); }
-            st = lst;
-            my = st.s >> 5; w = K1_UNALIGNED_ON ? st.s : my * 32;
-        } else {
-            const uint32_t t = ld_volatile(&ctrl[2]);
-            if (t == K1_DONE) { bar_arrive(bar_next, 64); return; }
-            if (t != my) {
-                if (t % NP != k) { bar_arrive(bar_next, 64); continue; }   // not mine: forward the token
-                my = t; w = my * 32; have = false;                 // jumped ahead to a window of mine
-            }
-            st.s = ld_volatile(&ctrl[3]); st.skip = ld_volatile(&ctrl[4]); st.rematch = ld_volatile(&ctrl[5]) != 0;
-            prod.head = ld_volatile(&ctrl[6]); prod.published = ld_volatile(&ctrl[7]);
-        }
+        const uint32_t w = st.s & ~31u;
         bool finished;
-        // fast-path test first: when it holds (w + 36 < s_limit, step 1) neither end-of-block test can
+        // fast-path test first: when it holds (w + 36 < s_limit, stride 1) neither end-of-block test can
         const bool fast = w + 36 < s_limit && (st.rematch || st.skip < 64);
         if (!fast && (st.rematch ? st.s >= s_limit : st.s + (st.skip >> 5) > s_limit)) finished = true;
         else {
             bool ok = false;
             if (fast) {
-                if (have) {
-                    const uint32_t cn = table[pre.h];
-                    if (any(lane >= st.s - w && cn != pre.c)) have = false;   // a slot I depend on moved: probe again
-                }
-                if (!have) {
-                    K1Seq nxt = seq;
-                    if (NP == 1 && w + 100 < n) nxt = k1_fetch_seq(win, w + 32);   // issue next window's loads now
-                    K1_TICK(0);                                      // [0] loop top / state checks / prefetch issue
-                    if (NP == 1 && GT && K1_GT_SPEC_ON && spec_w == w) pre = k1_eval<true>(win, table, shift, w, &seq K1_PROF_PASS, spec_c, st.s - w);
-                    else pre = k1_eval(win, table, shift, w, &seq K1_PROF_PASS);
-                    seq = nxt;
-                    if (NP == 1 && GT && K1_GT_SPEC_ON && seq.w == w + 32) {
-                        const unsigned nsh = (unsigned)((uintptr_t)(win + seq.w + lane) & 3u) * 8;
-                        spec_c = table[K1_HASH(funnel_r(seq.a0, seq.a1, nsh))];   // as of BEFORE this window's commit
-                        spec_w = seq.w;
-                    }
-                }
-#if defined(SB_EMU)
-                const uint32_t s_before = st.s;
-#endif
-                ok = k1_finish<GT>(win, n, table, shift, s_limit, st, ring, prod, pre, NP == 1 ? &seq : nullptr K1_PROF_PASS,
-                                   (NP == 1 && K1_UNALIGNED_ON) ? w : 0xFFFFFFFFu);
-#if defined(SB_EMU)
-                if (lane == 0) { if (ok) { g_k1_w32_stat[0]++; g_k1_w32_stat[1] += st.s - s_before; } else g_k1_w32_stat[2]++; }
-#endif
+                K1Seq nxt = seq;
+                if (w + 100 < n) nxt = k1_fetch_seq(win, w + 32);   // issue next window's loads now
+                K1_TICK(0);                                          // [0] loop top / state checks / prefetch issue
+                const K1Pre pre = k1_eval(win, table, shift, w, &seq K1_PROF_PASS);
+                seq = nxt;
+                ok = k1_finish<GT>(win, n, table, shift, s_limit, st, ring, prod, pre, &seq K1_PROF_PASS);
             }
             if (!ok) { K1_TICK(8); finished = k1_serial(win, n, table, shift, s_limit, st, w + 32, ring, prod); K1_TICK(9); }   // [9] serial path
             else finished = false;
@@ -597,31 +471,12 @@ SB_DEVICE void k1_parse_pipelined(const uint8_t* win, uint32_t n, uint16_t* tabl
         if (finished) {
             k1_push(ring, prod, k1_event(n, 0, 0));                // end marker -> trailing literal (:417-426)
             k1_publish(ring, prod);
+            K1_TICK(10);
+            K1_PROF_FLUSH;
+            syncwarp();
+            if (lane == 0) { ctrl[6] = prod.head; ctrl[7] = prod.published; }
+            return;
         }
-        if (NP == 1) {
-            lst = st;
-            if (finished) {
-                K1_TICK(10);
-                K1_PROF_FLUSH;
-                syncwarp();
-                if (lane == 0) { ctrl[6] = prod.head; ctrl[7] = prod.published; }
-                return;
-            }
-            my = 1;                                                // any non-zero value: "not the first window"
-            continue;
-        }
-        syncwarp();
-        if (lane == 0) {
-            ctrl[3] = st.s; ctrl[4] = st.skip; ctrl[5] = st.rematch ? 1u : 0u;
-            ctrl[6] = prod.head; ctrl[7] = prod.published;
-            ctrl[2] = finished ? K1_DONE : (st.s >> 5);
-        }
-        syncwarp();                                                // state visible to every lane / the next warp
-        if (NP > 1) {
-            bar_arrive(bar_next, 64);                              // pass the token on
-            if (finished) { bar_sync(bar_mine, 64); return; }      // absorb the token when it comes back round
-        } else if (finished) return;
-        my += NP;
     }
 }
 #undef K1_HASH
@@ -637,13 +492,10 @@ SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, c
     for (;;) {
         uint32_t avail;
         for (;;) {
-            // publish count BEFORE the head: if the head read is stale, the phase numbered `pubs` is still open
-            const uint32_t pubs = ring.mbar ? shfl(ld_volatile(&ring.ctrl[9]), 0) : 0;
             avail = ld_volatile(&ring.ctrl[0]) - tail;
             avail = shfl(avail, 0);
             if (avail) break;
-            if (ring.mbar) mbar_try_wait((uint64_t*)&ring.ctrl[10], pubs & 1u, 200000);
-            else spin_long();
+            spin_long();
         }
         const uint32_t m = avail < 32 ? avail : 32;
         threadfence_block();
@@ -709,76 +561,6 @@ SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, c
     }
 }
 
-// Kernel body: CTA = NP parser warps + one emitter warp, one unit (<= 65536 bytes) at a time.
-// flags bit0: write the varint(length) header in front of the block body.
-// GW = false: the block is staged into a shared-memory window (2 CTAs/SM).
-// GW = true : only the hash table and the event ring live in shared memory and the
-//             window is read in place from global memory/L2 (5 CTAs/SM).
-static const uint32_t K1_SMEM_BYTES_GW = K1_TABLE_BYTES + K1_RING_GW * 8 + 64;
-
-template <bool GW, int NP>
-SB_DEVICE void k1_compress_body(const BatchDesc& b, uint32_t flags) {
-    uint8_t* sm = smem();
-    uint8_t* win_s = sm;                                               // unused when GW
-    uint16_t* table = (uint16_t*)(sm + (GW ? 0 : K1_WIN_BYTES));
-    K1Ring ring;
-    ring.size = GW ? K1_RING_GW : K1_RING;
-    ring.ev = (uint64_t*)((uint8_t*)table + K1_TABLE_BYTES);
-    ring.ctrl = (uint32_t*)((uint8_t*)table + K1_TABLE_BYTES + ring.size * 8);
-    uint32_t* ctrl = ring.ctrl;
-    const unsigned lane = lane_id(), wid = warp_id(), nthreads = (NP + 1) * 32;
-    uint32_t tail = 0;                // emitter's private ring counter (never reset)
-    if (thread_idx() == 0) { ctrl[0] = 0; ctrl[1] = 0; ctrl[6] = 0; ctrl[7] = 0; }
-    for (uint32_t u = block_idx(); u < b.count; u += grid_dim()) {
-        const uint8_t* in = unit_in(b, u);
-        const uint32_t n = unit_in_len(b, u);
-        uint8_t* out = unit_out(b, u);
-        uint32_t d = 0;
-        if (flags & 1u) {                                                  // varint header (:120-128)
-            if (n == 0) { if (thread_idx() == 0) { out[0] = 0; b.out_lens[u] = 1; } continue; }
-            uint32_t v = n;
-            while (v >= 0x80) { if (thread_idx() == 0) out[d] = (uint8_t)v | 0x80; v >>= 7; d++; }
-            if (thread_idx() == 0) out[d] = (uint8_t)v;
-            d++;
-        }
-        if (n == 0) { if (thread_idx() == 0) b.out_lens[u] = d; continue; }
-        syncthreads();                                                     // previous unit fully drained
-        {
-            if (!GW) {
-                // stage the block: each warp copies one slice (cut on 16-byte boundaries)
-                const uint32_t per = ((n / (NP + 1)) + 15) & ~15u;
-                const uint32_t lo = per * wid < n ? per * wid : n;
-                const uint32_t hi = (wid == NP || lo + per > n) ? n : lo + per;
-                if (hi > lo) warp_copy(win_s + lo, in + lo, hi - lo);
-                if (thread_idx() < 16) ((uint32_t*)(win_s + ((n + 3) & ~3u)))[thread_idx()] = 0;   // defined bytes for over-reads
-            }
-            uint32_t tsize = 256;
-            while (tsize < 16384 && tsize < n) tsize *= 2;
-            for (uint32_t i = thread_idx(); i < tsize / 2; i += nthreads) ((uint32_t*)table)[i] = 0;   // (:514-516)
-            if (thread_idx() == 0) { ctrl[2] = n >= 17 ? 0u : K1_DONE; ctrl[3] = 1; ctrl[4] = 32; ctrl[5] = 0; }
-        }
-        syncthreads();
-        const uint8_t* win = GW ? in : win_s;
-        if (wid < (unsigned)NP) {
-            if (n >= 17) k1_parse_pipelined<NP>(win, n, table, ring, ctrl, wid);   // (:140-150)
-            else if (wid == 0) {                                           // tiny block: one literal (:140-146)
-                K1Prod prod;
-                prod.head = ctrl[6]; prod.published = ctrl[7]; prod.tail_seen = 0;
-                k1_push(ring, prod, k1_event(n, 0, 0));
-                k1_publish(ring, prod);
-                if (lane == 0) { ctrl[6] = prod.head; ctrl[7] = prod.published; }
-            }
-        } else {
-            d = k1_emit_block(win, out, d, ring, tail);
-            if (lane == 0) b.out_lens[u] = d;
-        }
-    }
-}
-
-}  // namespace sbk
-#include "k1_wide.cuh"   // experimental 64-position step (off unless -DK1_W64)
-#include "k1_exact.cuh"  // second-generation parser: exact windows, pipelined candidate evaluation
-namespace sbk {
 
 // One CTA per SM hosting NC + NG independent (parser, emitter) warp pairs. NC hash tables fill
 // the SM's shared memory (7 x 32KB); NG further chains keep their table in an L2-resident global
@@ -790,17 +572,17 @@ namespace sbk {
 // units from a shared counter (`work`, zeroed by the host before the launch) instead of a
 // fixed stride.
 //   ctrl[8] = the unit this pair works on
+// Unit limits (include/snapb200.h): a unit is one block, n <= 65536, and its output slot must hold
+// max_compress_len(n) bytes; a unit that violates either is skipped with out_lens = 0 and, when the batch has a
+// status array, TooBig / BufferTooSmall with the reference's payloads (src/compress.rs:104-117).
 template <bool GT>
 SB_DEVICE void k1_chain(const BatchDesc& b, uint32_t flags, uint16_t* table, const K1Ring& ring, uint32_t* ctrl,
-                        uint32_t* work, unsigned bar, uint32_t* scratch) {
+                        uint32_t* work, unsigned bar, uint32_t* crcs, const uint32_t* crc_tab) {
     const unsigned lane = lane_id(), wid = warp_id();
     const bool parser = (wid & 1u) == 0;
     const unsigned pt = (wid & 1u) * 32 + lane;                        // thread index within the pair
     uint32_t tail = 0;                // emitter's private ring counter (never reset)
-    if (pt == 0) {
-        ctrl[0] = 0; ctrl[1] = 0; ctrl[6] = 0; ctrl[7] = 0; ctrl[9] = 0;
-        if (ring.mbar) mbar_init((uint64_t*)&ctrl[10], 1);
-    }
+    if (pt == 0) { ctrl[0] = 0; ctrl[1] = 0; ctrl[6] = 0; ctrl[7] = 0; }
     for (;;) {
         if (pt == 0) ctrl[8] = atomic_add(work, 1u);
         bar_sync(bar, 64);                                                 // previous unit fully drained, next one chosen
@@ -809,6 +591,21 @@ SB_DEVICE void k1_chain(const BatchDesc& b, uint32_t flags, uint16_t* table, con
         const uint8_t* in = unit_in(b, u);
         const uint32_t n = unit_in_len(b, u);
         uint8_t* out = unit_out(b, u);
+        {
+            const uint32_t cap = unit_out_cap(b, u), need = 32u + n + n / 6u;   // max_compress_len (:42-53)
+            if (n > kMaxBlock || cap < need) {
+                if (pt == 0) {
+                    b.out_lens[u] = 0;
+                    if (b.statuses) {
+                        if (n > kMaxBlock) set_status(&b.statuses[u], SB_TOO_BIG, n, kMaxBlock, 0);
+                        else set_status(&b.statuses[u], SB_BUFFER_TOO_SMALL, cap, need, 0);
+                    }
+                }
+                bar_sync(bar, 64);
+                continue;
+            }
+        }
+        if (pt == 0 && b.statuses) set_status(&b.statuses[u], SB_OK, 0, 0, 0);
         uint32_t d = 0;
         if (flags & 1u) {                                                  // varint header (:120-128)
             uint32_t v = n;
@@ -816,7 +613,7 @@ SB_DEVICE void k1_chain(const BatchDesc& b, uint32_t flags, uint16_t* table, con
             if (pt == 0) out[d] = (uint8_t)v;
             d++;
         }
-        if (n == 0) { if (pt == 0) b.out_lens[u] = d; bar_sync(bar, 64); continue; }
+        if (n == 0) { if (pt == 0) { b.out_lens[u] = d; if (crcs) crcs[u] = 0; } bar_sync(bar, 64); continue; }
         {
             uint32_t tsize = 256;
             while (tsize < 16384 && tsize < n) tsize *= 2;
@@ -825,11 +622,7 @@ SB_DEVICE void k1_chain(const BatchDesc& b, uint32_t flags, uint16_t* table, con
         }
         bar_sync(bar, 64);
         if (parser) {
-            if (n >= 17) {                                                 // (:140-150)
-                if (K1_EXACT_ON && scratch) k1_parse_x<GT>(in, n, table, ring, ctrl, scratch);
-                else if (K1_W64_ON && (!GT || K1_W64_GT_ON)) k1_parse64<GT>(in, n, table, ring, ctrl);
-                else k1_parse_pipelined<1, GT>(in, n, table, ring, ctrl, 0);
-            }
+            if (n >= 17) k1_parse<GT>(in, n, table, ring, ctrl);           // (:140-150)
             else {                                                         // tiny block: one literal (:140-146)
                 K1Prod prod;
                 prod.head = ctrl[6]; prod.published = ctrl[7]; prod.tail_seen = 0;
@@ -838,35 +631,32 @@ SB_DEVICE void k1_chain(const BatchDesc& b, uint32_t flags, uint16_t* table, con
                 if (lane == 0) { ctrl[6] = prod.head; ctrl[7] = prod.published; }
             }
         } else {
+            // frame encode: the chunk's masked CRC-32C is computed here, beside the compress call (src/frame.rs:76),
+            // on issue slots the chain leaves idle while its parser produces the first events
+            if (crcs) { const uint32_t crc = k3_warp_crc32c_masked1(crc_tab, in, n); if (lane == 0) crcs[u] = crc; }
             d = k1_emit_block(in, out, d, ring, tail);
             if (lane == 0) b.out_lens[u] = d;
         }
     }
 }
 
-// shared memory of a multi-chain CTA: NC tables, 64 control bytes per chain, and (XS) the second-generation
-// parser's per-chain scratch (byte ring + info ring)
-constexpr size_t k1_multi_smem(int NC, int NG, bool XS) {
-    return (size_t)NC * K1_TABLE_BYTES + (size_t)(NC + NG) * 64 + (XS ? (size_t)(NC + NG) * K1X_SCRATCH_BYTES : 0);
-}
-template <int NC, int NG, bool XS = false>
+// shared memory of a multi-chain CTA: NC tables + 64 control bytes per chain + the CRC byte table
+constexpr size_t k1_multi_smem(int NC, int NG) { return (size_t)NC * K1_TABLE_BYTES + (size_t)(NC + NG) * 64 + K3_TABLE1_BYTES; }
+
+template <int NC, int NG>
 SB_DEVICE void k1_compress_body_multi(const BatchDesc& b, uint32_t flags, uint64_t* ring_scratch, uint16_t* gtables,
-                                      uint32_t* work) {
+                                      uint32_t* work, uint32_t* crcs) {
     uint8_t* sm = smem();
     const unsigned c = warp_id() >> 1;                                 // chain within the CTA
     uint32_t* ctrl = (uint32_t*)(sm + (size_t)NC * K1_TABLE_BYTES + c * 64);
-    uint32_t* scratch = XS ? (uint32_t*)(sm + (size_t)NC * K1_TABLE_BYTES + (size_t)(NC + NG) * 64 + (size_t)c * K1X_SCRATCH_BYTES) : nullptr;
+    uint32_t* crc_tab = (uint32_t*)(sm + (size_t)NC * K1_TABLE_BYTES + (size_t)(NC + NG) * 64);
+    if (crcs) { k3_build_table1(crc_tab, thread_idx(), block_dim()); syncthreads(); }
     K1Ring ring;
     ring.size = K1_RING_GW;
     ring.ev = ring_scratch + ((size_t)block_idx() * (NC + NG) + c) * K1_RING_GW;
     ring.ctrl = ctrl;
-#if defined(K1_MBAR)
-    ring.mbar = true;
-#elif defined(SB_EMU)
-    ring.mbar = (flags & 8u) != 0;
-#endif
-    if (NG == 0 || c < NC) k1_chain<false>(b, flags, (uint16_t*)(sm + (size_t)c * K1_TABLE_BYTES), ring, ctrl, work, 1 + c, scratch);
-    else k1_chain<true>(b, flags, gtables + ((size_t)block_idx() * NG + (c - NC)) * (K1_TABLE_BYTES / 2), ring, ctrl, work, 1 + c, scratch);
+    if (NG == 0 || c < NC) k1_chain<false>(b, flags, (uint16_t*)(sm + (size_t)c * K1_TABLE_BYTES), ring, ctrl, work, 1 + c, crcs, crc_tab);
+    else k1_chain<true>(b, flags, gtables + ((size_t)block_idx() * NG + (c - NC)) * (K1_TABLE_BYTES / 2), ring, ctrl, work, 1 + c, crcs, crc_tab);
 }
 
 }  // namespace sbk

@@ -219,7 +219,7 @@ SB_DEVICE uint32_t k2_decode_stream(const uint8_t* in, uint32_t n, uint8_t* dst,
                         srco[q] = e1;
                     }
 #pragma unroll
-                    for (int q = 0; q < 2; q++) v[q] = on[q] ? wout[(int)dsto[q] - (int)srco[q]] : (uint8_t)0;
+                    for (int q = 0; q < 2; q++) v[q] = on[q] ? wout[(int64_t)dsto[q] - (int64_t)srco[q]] : (uint8_t)0;   // offsets up to 2^32-1 are legal (:433-474)
 #pragma unroll
                     for (int q = 0; q < 2; q++) if (on[q]) wout[dsto[q]] = v[q];
                 }
@@ -235,8 +235,8 @@ SB_DEVICE uint32_t k2_decode_stream(const uint8_t* in, uint32_t n, uint8_t* dst,
                 if (coff >= clen || clen <= 32) {
                     // lanes below the offset read final bytes; an overlapping short copy is the
                     // periodic pattern of the last `coff` bytes (:306-317)
-                    if (lane < clen) out[lane] = out[(int)(coff >= clen || lane < coff ? lane : lane % coff) - (int)coff];
-                    if (clen > 32 && lane + 32 < clen) out[lane + 32] = out[(int)lane + 32 - (int)coff];
+                    if (lane < clen) out[lane] = out[(int64_t)(coff >= clen || lane < coff ? lane : lane % coff) - (int64_t)coff];
+                    if (clen > 32 && lane + 32 < clen) out[lane + 32] = out[(int64_t)lane + 32 - (int64_t)coff];
                 } else {
                     const uint8_t* from = out - coff;
                     for (uint32_t k = lane; k < clen; k += 32) out[k] = from[k % coff];

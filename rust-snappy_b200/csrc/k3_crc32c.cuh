@@ -91,6 +91,56 @@ SB_DEVICE uint32_t k3_warp_crc32c_masked(const uint32_t* tab, const uint8_t* p, 
     return ((crc >> 15) | (crc << 17)) + 0xA282EAD8u;   // src/crc32.rs:35-38
 }
 
+// ---- single-table variant for kernels that can spare only 1 KB of shared memory (K1's emitter warps:
+// frame encode computes the chunk checksum beside the compress call, reference src/frame.rs:76)
+static const uint32_t K3_TABLE1_BYTES = 256 * 4;
+// threads [t0, t0+nt) of the CTA build the byte table; the caller synchronises afterwards
+SB_DEVICE void k3_build_table1(uint32_t* tab, unsigned t, unsigned nt) {
+    for (uint32_t i = t; i < 256; i += nt) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ K3_POLY : c >> 1;
+        tab[i] = c;
+    }
+}
+SB_DEVICE uint32_t k3_word1(const uint32_t* tab, uint32_t st, uint32_t w) {
+    st ^= w;
+    st = tab[st & 0xFFu] ^ (st >> 8);
+    st = tab[st & 0xFFu] ^ (st >> 8);
+    st = tab[st & 0xFFu] ^ (st >> 8);
+    return tab[st & 0xFFu] ^ (st >> 8);
+}
+// raw CRC state over [p, p+n) with the byte table: 16-byte loads once p is 16-byte aligned
+SB_DEVICE uint32_t k3_slice1(const uint32_t* tab, uint32_t st, const uint8_t* p, uint32_t n) {
+    uint32_t head = (uint32_t)((0 - (uintptr_t)p) & 15u);
+    if (head > n) head = n;
+    st = k3_bytes(tab, st, p, head);
+    p += head; n -= head;
+    const uint4* v = (const uint4*)p;
+    const uint32_t nv = n >> 4;
+    for (uint32_t i = 0; i < nv; i++) {
+        const uint4 q = v[i];
+        st = k3_word1(tab, st, q.x); st = k3_word1(tab, st, q.y); st = k3_word1(tab, st, q.z); st = k3_word1(tab, st, q.w);
+    }
+    return k3_bytes(tab, st, p + 16 * nv, n & 15u);
+}
+// masked CRC-32C of [p, p+n) by the calling warp with the byte table; result in all lanes
+SB_DEVICE uint32_t k3_warp_crc32c_masked1(const uint32_t* tab, const uint8_t* p, uint32_t n) {
+    const unsigned lane = lane_id();
+    uint32_t sl = ((n + 31) / 32 + 15) & ~15u;     // slice length, multiple of 16
+    if (sl < 64) sl = 64;
+    uint64_t b0 = (uint64_t)lane * sl, b1 = b0 + sl;
+    if (b0 > n) b0 = n;
+    if (b1 > n) b1 = n;
+    uint32_t st = (lane == 0) ? 0xFFFFFFFFu : 0u;
+    st = k3_slice1(tab, st, p + b0, (uint32_t)(b1 - b0));
+    const uint32_t after = n - (uint32_t)b1;
+    if (after && st) st = k3_mulmod(k3_xpow8(after), st);
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) st ^= shfl_xor(st, k);
+    const uint32_t crc = ~st;
+    return ((crc >> 15) | (crc << 17)) + 0xA282EAD8u;   // src/crc32.rs:35-38
+}
+
 // Kernel body: warp w handles units w, w+nwarps, ...; out_lens[i] receives the masked CRC.
 SB_DEVICE void k3_crc_body(const BatchDesc& b) {
     uint32_t* tab = (uint32_t*)smem();

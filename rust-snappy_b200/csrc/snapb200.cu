@@ -11,53 +11,44 @@
 #include <cstring>
 #include <mutex>
 #include <vector>
+#include <sched.h>
 #include <time.h>
 
 #include "k1_compress.cuh"
 #include "k2_decompress.cuh"
 #include "k3_crc32c.cuh"
 #include "k4_frame.cuh"
+#include "k5_frame_decode.cuh"
 
 namespace {
 
 // ------------------------------------------------------------------ kernels
-// K1 variants: window in shared memory (S) or read in place from global/L2 (G) x parser warps per block
-__global__ void __launch_bounds__(64) k1_s1_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<false, 1>(b, flags); }
-__global__ void __launch_bounds__(96) k1_s2_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<false, 2>(b, flags); }
-__global__ void __launch_bounds__(128) k1_s3_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<false, 3>(b, flags); }
-__global__ void __launch_bounds__(160) k1_s4_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<false, 4>(b, flags); }
-__global__ void __launch_bounds__(64) k1_g1_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<true, 1>(b, flags); }
-__global__ void __launch_bounds__(96) k1_g2_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<true, 2>(b, flags); }
-__global__ void __launch_bounds__(128) k1_g3_kernel(sb_batch b, uint32_t flags) { sbk::k1_compress_body<true, 3>(b, flags); }
-// one CTA per SM: 7 parser/emitter pairs with their tables in shared memory + NG pairs with
+// K1: one CTA per SM: 7 parser/emitter pairs with their tables in shared memory + NG pairs with
 // their tables in an L2-resident scratch; rings in global scratch; units taken from `work`
 template <int NG>
 __global__ void __launch_bounds__((7 + NG) * 64, 1)
-k1_m7_kernel(sb_batch b, uint32_t flags, uint64_t* rings, uint16_t* gtables, uint32_t* work) {
-    sbk::k1_compress_body_multi<7, NG>(b, flags, rings, gtables, work);
+k1_m7_kernel(sb_batch b, uint32_t flags, uint64_t* rings, uint16_t* gtables, uint32_t* work, uint32_t* crcs) {
+    sbk::k1_compress_body_multi<7, NG>(b, flags, rings, gtables, work, crcs);
 }
-// second-generation parser (k1_exact.cuh): 6 shared-memory tables + per-chain byte/info rings, NG chains with L2 tables
-template <int NG>
-__global__ void __launch_bounds__((6 + NG) * 64, 1)
-k1_x_kernel(sb_batch b, uint32_t flags, uint64_t* rings, uint16_t* gtables, uint32_t* work) {
-    sbk::k1_compress_body_multi<6, NG, true>(b, flags, rings, gtables, work);
-}
-const int K1X_MAX_NG = 10;
 const int K1_MAX_NG = 7;
-const size_t K1_M7_SMEM = 7 * sbk::K1_TABLE_BYTES + (7 + K1_MAX_NG) * 64;
+const size_t K1_M7_SMEM = sbk::k1_multi_smem(7, K1_MAX_NG);
 __global__ void __launch_bounds__(128) k2_decompress_kernel(sb_batch b) { sbk::k2_decompress_body(b); }
 __global__ void __launch_bounds__(256) k3_crc_kernel(sb_batch b) { sbk::k3_crc_body(b); }
-__global__ void __launch_bounds__(256) k4_sizes_kernel(sbk::FramePlan p) { sbk::k4_sizes_body(p); }
-__global__ void __launch_bounds__(1024) k4_scan_kernel(sbk::FramePlan p) { sbk::k4_scan_body(p); }
+__global__ void __launch_bounds__(256) k4_fill_lens_kernel(uint32_t* lens, uint64_t n, uint32_t nchunks) { sbk::k4_fill_lens_body(lens, n, nchunks); }
+__global__ void __launch_bounds__(1024) k4_scan_local_kernel(sbk::FramePlan p) { sbk::k4_scan_local_body(p); }
+__global__ void __launch_bounds__(1024) k4_scan_tiles_kernel(sbk::FramePlan p) { sbk::k4_scan_tiles_body(p); }
 __global__ void __launch_bounds__(256) k4_gather_kernel(sbk::FramePlan p) { sbk::k4_gather_body(p); }
-__global__ void __launch_bounds__(256) k5_copy_units_kernel(sb_batch b) { sbk::k5_copy_units_body(b); }
+__global__ void __launch_bounds__(256) k5_parse_kernel(sbk::DecodePlan p) { sbk::k5_parse_body(p); }
+__global__ void __launch_bounds__(32) k5_walk_kernel(sbk::DecodePlan p) { sbk::k5_walk_body(p); }
+__global__ void __launch_bounds__(1024) k5_scan_local_kernel(sbk::DecodePlan p) { sbk::k5_scan_local_body(p); }
+__global__ void __launch_bounds__(1024) k5_scan_tiles_kernel(sbk::DecodePlan p) { sbk::k5_scan_tiles_body(p); }
+__global__ void __launch_bounds__(128) k5_decode_kernel(sbk::DecodePlan p) { sbk::k5_decode_body(p); }
+__global__ void __launch_bounds__(32) k5_finish_kernel(sbk::DecodePlan p) { sbk::k5_finish_body(p); }
 __global__ void __launch_bounds__(256) k6_generate_kernel(sbk::GenPlan g) { sbk::k6_generate_body(g); }
 
 std::atomic<uint64_t> g_launches{0};
-const int K1_DEFAULT_NP = 1;
+std::atomic<uint64_t> g_allocs{0};     // cudaMalloc / cudaHostAlloc / event + stream creations since load
 const int K2_DEFAULT_CTAS_PER_SM = 16;
-const int K1_DEFAULT_GW = 1;
-const int K1_DEFAULT_MULTI = 1;
 const int K1_DEFAULT_NG = 5;
 
 int fail(sb_error* e, uint32_t code, uint64_t a = 0, uint64_t b = 0, uint64_t c = 0) {
@@ -78,6 +69,7 @@ void ok(sb_error* e) { if (e) { e->code = 0; e->_pad = 0; e->a = e->b = e->c = 0
     } while (0)
 
 // ------------------------------------------------------------- device state
+// Grow-only pools: the first calls size them (or sb_reserve does), the steady state allocates nothing.
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -85,6 +77,7 @@ struct DevBuf {
         if (n <= cap) return cudaSuccess;
         if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
         size_t want = n + n / 8 + 4096;
+        g_allocs++;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { e = cudaMalloc(&p, n); want = n; }
         if (e == cudaSuccess) cap = want;
@@ -95,49 +88,68 @@ struct DevBuf {
 
 struct Ctx {
     int dev = -1, sms = 0;
-    bool ready = false;
+    std::atomic<bool> ready{false};
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     DevBuf rings, gtables, work;   // K1 scratch: event rings, L2-resident tables, unit counter
     cudaEvent_t k1_done = nullptr; // K1 launches share that scratch: each waits for the previous one, whatever its stream
     std::mutex k1_mu;
-    DevBuf in[2], slots[2], compact[2], lens[2], csize[2], offs[2], crcs[2], status[2], ptrs_in[2], ptrs_out[2], caps[2];
-    void* pinned[4] = {nullptr, nullptr, nullptr, nullptr}; size_t pinned_cap[4] = {0, 0, 0, 0};   // pinned staging: [0,1] descriptors in, [2,3] results out
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};   // host-batch pipeline
+    DevBuf in[2], slots[2], compact[2], lens[2], status[2], ptrs_in[2], ptrs_out[2], caps[2], ws[2];
+    void* pinned[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // pinned staging: [0,1] descriptors in, [2,3] results out, [4] scalar results
+    size_t pinned_cap[5] = {0, 0, 0, 0, 0};
     std::mutex mu;
 };
 Ctx g_ctx[16];
+std::mutex g_init_mu;
 
+int init_ctx(Ctx& c, int dev, sb_error* err) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    c.dev = dev; c.sms = prop.multiProcessorCount;
+    CK(cudaFuncSetAttribute(k1_m7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
+    CK(cudaFuncSetAttribute(k1_m7_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
+    CK(cudaFuncSetAttribute(k1_m7_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
+    CK(c.rings.need((size_t)c.sms * (7 + K1_MAX_NG) * sbk::K1_RING_GW * 8));
+    CK(c.gtables.need((size_t)c.sms * K1_MAX_NG * sbk::K1_TABLE_BYTES));
+    CK(c.work.need(256));
+    g_allocs += 10;
+    CK(cudaEventCreateWithFlags(&c.k1_done, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) {
+        CK(cudaEventCreateWithFlags(&c.ev_in[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.ev_k[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.ev_out[k], cudaEventDisableTiming));
+    }
+    CK(cudaStreamCreateWithFlags(&c.s_compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking));
+    return 0;
+}
+void destroy_partial(Ctx& c) {
+    if (c.k1_done) { cudaEventDestroy(c.k1_done); c.k1_done = nullptr; }
+    for (int k = 0; k < 2; k++) {
+        if (c.ev_in[k]) { cudaEventDestroy(c.ev_in[k]); c.ev_in[k] = nullptr; }
+        if (c.ev_k[k]) { cudaEventDestroy(c.ev_k[k]); c.ev_k[k] = nullptr; }
+        if (c.ev_out[k]) { cudaEventDestroy(c.ev_out[k]); c.ev_out[k] = nullptr; }
+    }
+    if (c.s_compute) { cudaStreamDestroy(c.s_compute); c.s_compute = nullptr; }
+    if (c.s_h2d) { cudaStreamDestroy(c.s_h2d); c.s_h2d = nullptr; }
+    if (c.s_d2h) { cudaStreamDestroy(c.s_d2h); c.s_d2h = nullptr; }
+}
+
+// First use per device is serialised (two threads making their first call together run one initialisation);
+// a failed initialisation is undone and retried by the next call.
 int get_ctx(Ctx** out, sb_error* err) {
     int dev = 0;
     CK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 16) return fail(err, SB_E_NO_DEVICE);
     Ctx& c = g_ctx[dev];
-    if (!c.ready) {
-        cudaDeviceProp prop;
-        CK(cudaGetDeviceProperties(&prop, dev));
-        c.dev = dev; c.sms = prop.multiProcessorCount;
-        CK(cudaFuncSetAttribute(k1_s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES));
-        CK(cudaFuncSetAttribute(k1_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES));
-        CK(cudaFuncSetAttribute(k1_s3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES));
-        CK(cudaFuncSetAttribute(k1_s4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES));
-        CK(cudaFuncSetAttribute(k1_g1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
-        CK(cudaFuncSetAttribute(k1_g2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
-        CK(cudaFuncSetAttribute(k1_g3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::K1_SMEM_BYTES_GW));
-        CK(cudaFuncSetAttribute(k1_m7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
-        CK(cudaFuncSetAttribute(k1_m7_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
-        CK(cudaFuncSetAttribute(k1_m7_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_M7_SMEM));
-        CK(cudaFuncSetAttribute(k1_x_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::k1_multi_smem(6, 0, true)));
-        CK(cudaFuncSetAttribute(k1_x_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::k1_multi_smem(6, 4, true)));
-        CK(cudaFuncSetAttribute(k1_x_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::k1_multi_smem(6, 6, true)));
-        CK(cudaFuncSetAttribute(k1_x_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::k1_multi_smem(6, 8, true)));
-        CK(cudaFuncSetAttribute(k1_x_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbk::k1_multi_smem(6, 10, true)));
-        CK(c.rings.need((size_t)c.sms * 16 * sbk::K1_RING_GW * 8));
-        CK(c.gtables.need((size_t)c.sms * K1X_MAX_NG * sbk::K1_TABLE_BYTES));
-        CK(c.work.need(256));
-        CK(cudaEventCreateWithFlags(&c.k1_done, cudaEventDisableTiming));
-        CK(cudaStreamCreateWithFlags(&c.s_compute, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking));
-        c.ready = true;
+    if (!c.ready.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lk(g_init_mu);
+        if (!c.ready.load(std::memory_order_relaxed)) {
+            const int rc = init_ctx(c, dev, err);
+            if (rc) { destroy_partial(c); return rc; }
+            c.ready.store(true, std::memory_order_release);
+        }
     }
     *out = &c;
     return 0;
@@ -149,74 +161,35 @@ int need_pinned(Ctx& c, int slot, size_t n, sb_error* err) {
     if (n <= c.pinned_cap[slot]) return 0;
     if (c.pinned[slot]) { CK(cudaFreeHost(c.pinned[slot])); c.pinned[slot] = nullptr; c.pinned_cap[slot] = 0; }
     n += n / 4 + 4096;
+    g_allocs++;
     CK(cudaHostAlloc(&c.pinned[slot], n, cudaHostAllocDefault));
     c.pinned_cap[slot] = n;
     return 0;
 }
 
 // ------------------------------------------------------------ launch helpers
-int launch_k1(Ctx& c, const sb_batch& b, uint32_t flags, cudaStream_t st, sb_error* err) {
+int launch_k1(Ctx& c, const sb_batch& b, uint32_t flags, uint32_t* crcs, cudaStream_t st, sb_error* err) {
     if (b.count == 0) return 0;
-    // K1 variant: SNAPB200_K1_GW=1 (default) reads the window in place from global/L2 (6 CTAs/SM instead of 2),
-    // SNAPB200_K1_NP = parser warps per block (pipelined over windows).
-    static const int gw = getenv("SNAPB200_K1_GW") ? atoi(getenv("SNAPB200_K1_GW")) : K1_DEFAULT_GW;
-    static const int np = getenv("SNAPB200_K1_NP") ? atoi(getenv("SNAPB200_K1_NP")) : K1_DEFAULT_NP;
-    unsigned grid = (unsigned)((gw ? 6 : 2) * c.sms);
-    if (grid > b.count) grid = b.count;
-    const size_t sm = gw ? sbk::K1_SMEM_BYTES_GW : sbk::K1_SMEM_BYTES;
-    static const int multi = getenv("SNAPB200_K1_MULTI") ? atoi(getenv("SNAPB200_K1_MULTI")) : K1_DEFAULT_MULTI;
-    static const int xmode = getenv("SNAPB200_K1_X") ? atoi(getenv("SNAPB200_K1_X")) : 1;
-    if (xmode) {
-        // SNAPB200_K1_NG = chains per SM with L2-resident tables next to the 6 shared-memory ones (0..10)
-        static const int ng_env = getenv("SNAPB200_K1_NG") ? atoi(getenv("SNAPB200_K1_NG")) : 6;
-        const unsigned ng = ng_env < 0 ? 0 : ng_env > K1X_MAX_NG ? K1X_MAX_NG : (unsigned)ng_env;
-        unsigned chains = (unsigned)(((uint64_t)b.count + c.sms - 1) / c.sms);
-        if (chains > 6 + ng) chains = 6 + ng;
-        unsigned mg = (unsigned)c.sms;
-        if (mg > b.count) mg = b.count;
-        std::lock_guard<std::mutex> k1lk(c.k1_mu);
-        CK(cudaStreamWaitEvent(st, c.k1_done, 0));
-        CK(cudaMemsetAsync(c.work.p, 0, 4, st));
-        uint64_t* rg = c.rings.as<uint64_t>(); uint16_t* gt = c.gtables.as<uint16_t>(); uint32_t* wk = c.work.as<uint32_t>();
-        // the template argument bounds the chain count (launch bounds / register cap, scratch strides)
-        if (ng > 8) k1_x_kernel<10><<<mg, chains * 64, sbk::k1_multi_smem(6, 10, true), st>>>(b, flags, rg, gt, wk);
-        else if (ng > 6) k1_x_kernel<8><<<mg, chains * 64, sbk::k1_multi_smem(6, 8, true), st>>>(b, flags, rg, gt, wk);
-        else if (ng > 4) k1_x_kernel<6><<<mg, chains * 64, sbk::k1_multi_smem(6, 6, true), st>>>(b, flags, rg, gt, wk);
-        else if (ng > 0) k1_x_kernel<4><<<mg, chains * 64, sbk::k1_multi_smem(6, 4, true), st>>>(b, flags, rg, gt, wk);
-        else k1_x_kernel<0><<<mg, chains * 64, sbk::k1_multi_smem(6, 0, true), st>>>(b, flags, rg, gt, wk);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(c.k1_done, st));
-    } else if (multi) {
-        // SNAPB200_K1_NG = extra chains per SM with L2-resident tables (0..7)
-        static const int ng_env = getenv("SNAPB200_K1_NG") ? atoi(getenv("SNAPB200_K1_NG")) : K1_DEFAULT_NG;
-        const unsigned ng = ng_env < 0 ? 0 : ng_env > K1_MAX_NG ? K1_MAX_NG : (unsigned)ng_env;
-        // small batches spread over the SMs first (one shared-memory-table chain per SM is the fastest a block can
-        // run); only batches with more units than that stack chains on an SM, L2-table chains last
-        unsigned chains = (unsigned)(((uint64_t)b.count + c.sms - 1) / c.sms);
-        if (chains > 7 + ng) chains = 7 + ng;
-        unsigned mg = (unsigned)c.sms;
-        if (mg > b.count) mg = b.count;
-        std::lock_guard<std::mutex> k1lk(c.k1_mu);
-        CK(cudaStreamWaitEvent(st, c.k1_done, 0));
-        CK(cudaMemsetAsync(c.work.p, 0, 4, st));
-        // the template argument only bounds the chain count (launch bounds / register cap, scratch strides)
-        if (ng > 5) k1_m7_kernel<7><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
-        else if (ng > 0) k1_m7_kernel<5><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
-        else k1_m7_kernel<0><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, c.rings.as<uint64_t>(), c.gtables.as<uint16_t>(), c.work.as<uint32_t>());
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(c.k1_done, st));
-    } else if (gw) {
-        if (np <= 1) k1_g1_kernel<<<grid, 64, sm, st>>>(b, flags);
-        else if (np == 2) k1_g2_kernel<<<grid, 96, sm, st>>>(b, flags);
-        else k1_g3_kernel<<<grid, 128, sm, st>>>(b, flags);
-    } else {
-        if (np <= 1) k1_s1_kernel<<<grid, 64, sm, st>>>(b, flags);
-        else if (np == 2) k1_s2_kernel<<<grid, 96, sm, st>>>(b, flags);
-        else if (np == 3) k1_s3_kernel<<<grid, 128, sm, st>>>(b, flags);
-        else k1_s4_kernel<<<grid, 160, sm, st>>>(b, flags);
-    }
-    g_launches++;
+    // SNAPB200_K1_NG = chains per SM with L2-resident tables next to the 7 shared-memory ones (0..7)
+    static const int ng_env = getenv("SNAPB200_K1_NG") ? atoi(getenv("SNAPB200_K1_NG")) : K1_DEFAULT_NG;
+    const unsigned ng = ng_env < 0 ? 0 : ng_env > K1_MAX_NG ? K1_MAX_NG : (unsigned)ng_env;
+    // small batches spread over the SMs first (one shared-memory-table chain per SM is the fastest a block can
+    // run); only batches with more units than that stack chains on an SM, L2-table chains last
+    unsigned chains = (unsigned)(((uint64_t)b.count + c.sms - 1) / c.sms);
+    if (chains > 7 + ng) chains = 7 + ng;
+    unsigned mg = (unsigned)c.sms;
+    if (mg > b.count) mg = b.count;
+    std::lock_guard<std::mutex> k1lk(c.k1_mu);
+    CK(cudaStreamWaitEvent(st, c.k1_done, 0));
+    CK(cudaMemsetAsync(c.work.p, 0, 4, st));
+    uint64_t* rg = c.rings.as<uint64_t>(); uint16_t* gt = c.gtables.as<uint16_t>(); uint32_t* wk = c.work.as<uint32_t>();
+    // the template argument only bounds the chain count (launch bounds / register cap, scratch strides)
+    if (ng > 5) k1_m7_kernel<7><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, rg, gt, wk, crcs);
+    else if (ng > 0) k1_m7_kernel<5><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, rg, gt, wk, crcs);
+    else k1_m7_kernel<0><<<mg, chains * 64, K1_M7_SMEM, st>>>(b, flags, rg, gt, wk, crcs);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c.k1_done, st));
+    g_launches++;
     return 0;
 }
 int launch_k2(Ctx& c, const sb_batch& b, cudaStream_t st, sb_error* err) {
@@ -244,21 +217,12 @@ int launch_k3(Ctx& c, const sb_batch& b, cudaStream_t st, sb_error* err) {
     CK(cudaGetLastError());
     return 0;
 }
-int launch_copy_units(Ctx& c, const sb_batch& b, cudaStream_t st, sb_error* err) {
-    if (b.count == 0) return 0;
-    uint64_t blocks = ((uint64_t)b.count + 7) / 8;
-    unsigned grid = (unsigned)(8 * c.sms);
-    if (grid > blocks) grid = (unsigned)blocks;
-    k5_copy_units_kernel<<<grid, 256, 0, st>>>(b);
-    g_launches++;
-    CK(cudaGetLastError());
-    return 0;
-}
-// sizes -> scan -> gather over a FramePlan whose slots/clens(/crcs) are filled
+// scan (tile-local, tiles) -> gather over a FramePlan whose slots/clens(/crcs) are filled
 int launch_assemble(Ctx& c, const sbk::FramePlan& p, cudaStream_t st, sb_error* err) {
     if (p.nchunks == 0) return 0;
-    k4_sizes_kernel<<<(p.nchunks + 255) / 256, 256, 0, st>>>(p);
-    k4_scan_kernel<<<1, 1024, 1024 * sizeof(uint64_t), st>>>(p);
+    const unsigned ntiles = (p.nchunks + sbk::K4_TILE - 1) / sbk::K4_TILE;
+    k4_scan_local_kernel<<<ntiles, sbk::K4_TILE, 32 * sizeof(uint32_t), st>>>(p);
+    k4_scan_tiles_kernel<<<1, 1024, 1024 * sizeof(uint64_t), st>>>(p);
     uint64_t blocks = ((uint64_t)p.nchunks + 7) / 8;
     unsigned grid = (unsigned)(8 * c.sms);
     if (grid > blocks) grid = (unsigned)blocks;
@@ -292,61 +256,111 @@ const uint64_t SB_MAX_INPUT = 0xFFFFFFFFull;
 const uint32_t SB_MAX_BLOCK = 65536;
 const uint32_t SB_MAX_CBLOCK = 76490;   // reference src/frame.rs:12
 
-// Device-resident compress of one logical stream of n bytes at d_in into the
-// final layout at d_out: frame=0 -> raw stream (varint + blocks), frame=1 ->
-// frame chunks (optionally preceded by the stream identifier). wave buffers b=0.
-int compress_stream_device(Ctx& c, const uint8_t* d_in, uint64_t n, uint8_t* d_out, int frame, int ident,
-                           uint64_t* total_out, cudaStream_t st, sb_error* err) {
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- workspace layouts (caller-provided or pooled scratch; every sub-array 256-byte aligned)
+struct EncodeWs { uint8_t* slots; uint32_t *lens_in, *clens, *crcs; uint64_t *offs, *tiles; };
+uint64_t encode_ws_bytes(uint64_t n) {
+    const uint64_t nchunks = (n + SB_MAX_BLOCK - 1) / SB_MAX_BLOCK;
+    return align_up(nchunks * (uint64_t)sbk::kSlotStride, 256) + 3 * align_up(nchunks * 4 + 4, 256) +
+           align_up((nchunks + 1) * 8, 256) + align_up((nchunks / sbk::K4_TILE + 3) * 8, 256) + 256;
+}
+EncodeWs carve_encode_ws(void* scratch, uint64_t nchunks) {
+    uint8_t* p = (uint8_t*)align_up((size_t)scratch, 256);
+    EncodeWs w;
+    w.slots = p; p += align_up(nchunks * (uint64_t)sbk::kSlotStride, 256);
+    w.lens_in = (uint32_t*)p; p += align_up(nchunks * 4 + 4, 256);
+    w.clens = (uint32_t*)p; p += align_up(nchunks * 4 + 4, 256);
+    w.crcs = (uint32_t*)p; p += align_up(nchunks * 4 + 4, 256);
+    w.offs = (uint64_t*)p; p += align_up((nchunks + 1) * 8, 256);
+    w.tiles = (uint64_t*)p;
+    return w;
+}
+
+// Stream-ordered compress of one logical stream of n bytes at d_in into the final layout at d_out:
+// frame=0 -> raw stream (varint + blocks), frame=1 -> frame chunks (optionally preceded by the stream
+// identifier). No host synchronisation for n > 0; the outcome lands in *d_result (device).
+int compress_stream_ws(Ctx& c, const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap, int frame, int ident,
+                       uint64_t* d_chunk_offs, sb_frame_result* d_result, void* scratch, cudaStream_t st, sb_error* err) {
     const uint64_t nchunks64 = (n + SB_MAX_BLOCK - 1) / SB_MAX_BLOCK;
     if (nchunks64 > 0xFFFFFFFFull) return fail(err, SB_TOO_BIG, n, SB_MAX_INPUT);
     const uint32_t nchunks = (uint32_t)nchunks64;
-    uint8_t head[16];
-    size_t head_len = 0;
-    if (frame) { if (ident && n) { memcpy(head, "\xff\x06\x00\x00sNaPpY", 10); head_len = 10; } }
-    else head_len = put_varint(head, n);
+    sbk::FramePlan p;
+    memset(&p, 0, sizeof p);
+    if (frame) { if (ident && n) { memcpy(p.head, "\xff\x06\x00\x00sNaPpY", 10); p.head_len = 10; } }
+    else p.head_len = (uint32_t)put_varint(p.head, n);
     if (n == 0) {
-        if (head_len) CK(cudaMemcpyAsync(d_out, head, head_len, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
-        *total_out = head_len;
+        // nothing to compress: the prefix (raw: the one-byte varint; frame: nothing, src/write.rs:155-157) and the result
+        sb_frame_result r;
+        memset(&r, 0, sizeof r);
+        r.bytes = p.head_len;
+        if (p.head_len > cap) { r.status.code = SB_BUFFER_TOO_SMALL; r.status.a = cap; r.status.b = p.head_len; r.bytes = 0; }
+        else if (p.head_len) CK(cudaMemcpyAsync(d_out, p.head, p.head_len, cudaMemcpyHostToDevice, st));
+        if (d_result) CK(cudaMemcpyAsync(d_result, &r, sizeof r, cudaMemcpyHostToDevice, st));
+        if (d_chunk_offs) { const uint64_t z = p.head_len; CK(cudaMemcpyAsync(d_chunk_offs, &z, 8, cudaMemcpyHostToDevice, st)); }
+        CK(cudaStreamSynchronize(st));   // the sources above are on this stack frame
         return 0;
     }
-    CK(c.slots[0].need((size_t)nchunks * sbk::kSlotStride));
-    CK(c.lens[0].need((size_t)nchunks * 4 + 4));
-    CK(c.csize[0].need((size_t)nchunks * 4 + 4));
-    CK(c.offs[0].need(((size_t)nchunks + 1) * 8));
-    CK(c.crcs[0].need((size_t)nchunks * 4 + 4));
-    CK(c.caps[0].need((size_t)nchunks * 4 + 4));
-    // per-chunk input lengths: all 65536 except the last
-    {
-        std::vector<uint32_t> lens(nchunks, SB_MAX_BLOCK);
-        lens[nchunks - 1] = (uint32_t)(n - (uint64_t)(nchunks - 1) * SB_MAX_BLOCK);
-        CK(cudaMemcpyAsync(c.caps[0].p, lens.data(), (size_t)nchunks * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));   // `lens` is a temporary
-    }
+    const EncodeWs w = carve_encode_ws(scratch, nchunks);
+    k4_fill_lens_kernel<<<(nchunks + 255) / 256, 256, 0, st>>>(w.lens_in, n, nchunks);
+    g_launches++;
     sb_batch b;
     memset(&b, 0, sizeof b);
-    b.in_base = d_in; b.in_stride = SB_MAX_BLOCK; b.in_lens = c.caps[0].as<uint32_t>();
-    b.out_base = c.slots[0].as<uint8_t>(); b.out_stride = sbk::kSlotStride; b.out_cap_uniform = sbk::kSlotStride;
-    b.out_lens = c.lens[0].as<uint32_t>(); b.count = nchunks;
-    int rc = launch_k1(c, b, frame ? 1u : 0u, st, err);   // frame chunks carry their own varint
+    b.in_base = d_in; b.in_stride = SB_MAX_BLOCK; b.in_lens = w.lens_in;
+    b.out_base = w.slots; b.out_stride = sbk::kSlotStride; b.out_cap_uniform = sbk::kSlotStride;
+    b.out_lens = w.clens; b.count = nchunks;
+    int rc = launch_k1(c, b, frame ? 1u : 0u, frame ? w.crcs : nullptr, st, err);   // frame chunks carry their own varint
     if (rc) return rc;
-    if (frame) {
-        sb_batch cb = b;
-        cb.out_lens = c.crcs[0].as<uint32_t>();
-        rc = launch_k3(c, cb, st, err);
-        if (rc) return rc;
-    }
-    sbk::FramePlan p;
-    p.in = d_in; p.n = n; p.slots = c.slots[0].as<uint8_t>(); p.clens = c.lens[0].as<uint32_t>();
-    p.crcs = c.crcs[0].as<uint32_t>(); p.nchunks = nchunks; p.frame = frame ? 1u : 0u; p.base = head_len;
-    p.csize = c.csize[0].as<uint32_t>(); p.offs = c.offs[0].as<uint64_t>(); p.out = d_out;
-    rc = launch_assemble(c, p, st, err);
-    if (rc) return rc;
-    if (head_len) CK(cudaMemcpyAsync(d_out, head, head_len, cudaMemcpyHostToDevice, st));
-    uint64_t total = 0;
-    CK(cudaMemcpyAsync(&total, c.offs[0].as<uint64_t>() + nchunks, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    *total_out = total;
+    p.in = d_in; p.n = n; p.slots = w.slots; p.clens = w.clens; p.crcs = w.crcs; p.nchunks = nchunks;
+    p.frame = frame ? 1u : 0u; p.offs = d_chunk_offs ? d_chunk_offs : w.offs; p.tiles = w.tiles;
+    p.out = d_out; p.cap = cap; p.result = d_result;
+    return launch_assemble(c, p, st, err);
+}
+
+// ---- frame decode
+struct DecodeWs { sbk::FChunk* chunks; uint64_t *ooff, *tiles; sb_error* statuses; sbk::DecodeCtl* ctl; };
+uint64_t decode_ws_bytes(uint64_t max_chunks) {
+    return align_up(max_chunks * sizeof(sbk::FChunk) + 64, 256) + align_up((max_chunks + 1) * 8, 256) +
+           align_up((max_chunks / sbk::K4_TILE + 3) * 8, 256) + align_up(max_chunks * sizeof(sb_error) + 64, 256) + 512;
+}
+DecodeWs carve_decode_ws(void* scratch, uint64_t max_chunks) {
+    uint8_t* p = (uint8_t*)align_up((size_t)scratch, 256);
+    DecodeWs w;
+    w.chunks = (sbk::FChunk*)p; p += align_up(max_chunks * sizeof(sbk::FChunk) + 64, 256);
+    w.ooff = (uint64_t*)p; p += align_up((max_chunks + 1) * 8, 256);
+    w.tiles = (uint64_t*)p; p += align_up((max_chunks / sbk::K4_TILE + 3) * 8, 256);
+    w.statuses = (sb_error*)p; p += align_up(max_chunks * sizeof(sb_error) + 64, 256);
+    w.ctl = (sbk::DecodeCtl*)p;
+    return w;
+}
+sbk::DecodePlan make_decode_plan(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap, const uint64_t* d_index,
+                                 uint32_t index_n, int fragment, sb_frame_result* d_result, void* scratch, uint32_t max_chunks) {
+    const DecodeWs w = carve_decode_ws(scratch, max_chunks);
+    sbk::DecodePlan p;
+    memset(&p, 0, sizeof p);
+    p.in = d_in; p.n = n; p.index = d_index; p.index_n = d_index ? index_n : 0; p.fragment = fragment ? 1u : 0u;
+    p.chunks = w.chunks; p.cap_chunks = max_chunks; p.ooff = w.ooff; p.tiles = w.tiles; p.statuses = w.statuses; p.ctl = w.ctl;
+    p.out = d_out; p.cap = cap; p.result = d_result;
+    return p;
+}
+// phase 1: chunk table + output offsets (ctl->produced, ctl->go valid afterwards)
+int decode_index_phase(Ctx& c, const sbk::DecodePlan& p, cudaStream_t st, sb_error* err) {
+    CK(cudaMemsetAsync(p.ctl, 0, sizeof(sbk::DecodeCtl), st));
+    if (p.index) { k5_parse_kernel<<<p.index_n ? (p.index_n + 255) / 256 : 1, 256, 0, st>>>(p); g_launches++; }
+    k5_walk_kernel<<<1, 32, 0, st>>>(p);
+    const unsigned ntiles = (p.cap_chunks + sbk::K4_TILE - 1) / sbk::K4_TILE;
+    k5_scan_local_kernel<<<ntiles ? ntiles : 1, sbk::K4_TILE, 32 * sizeof(uint32_t), st>>>(p);
+    k5_scan_tiles_kernel<<<1, 1024, 1024 * sizeof(uint64_t), st>>>(p);
+    g_launches += 3;
+    CK(cudaGetLastError());
+    return 0;
+}
+// phase 2: payload decode + checksum + result
+int decode_payload_phase(Ctx& c, const sbk::DecodePlan& p, cudaStream_t st, sb_error* err) {
+    k5_decode_kernel<<<16 * c.sms, 128, sbk::K3_TABLE_BYTES + 4 * sbk::K2_SMEM_PER_WARP, st>>>(p);
+    k5_finish_kernel<<<1, 32, 0, st>>>(p);
+    g_launches += 2;
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -355,8 +369,9 @@ int compress_stream_device(Ctx& c, const uint8_t* d_in, uint64_t n, uint8_t* d_o
 // =========================================================================
 extern "C" {
 
-const char* sb_version(void) { return "snapb200 0.1 (sm_100a)"; }
+const char* sb_version(void) { return "snapb200 0.2 (sm_100a)"; }
 uint64_t sb_launch_count(void) { return g_launches.load(); }
+uint64_t sb_alloc_count(void) { return g_allocs.load(); }
 
 size_t sb_max_compress_len(size_t input_len) {
     uint64_t n = (uint64_t)input_len;
@@ -370,6 +385,68 @@ size_t sb_frame_max_len(size_t n) {
     return 10 + chunks * (8 + (size_t)SB_MAX_CBLOCK);
 }
 
+// Pin the calling thread to the CPUs of the NUMA node the device hangs off, so that its pinned allocations and
+// staging copies stay local (a rank per GPU on a two-socket box otherwise streams through the far socket).
+int sb_bind_host_thread_to_device_numa(int device) {
+    char bus[32];
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return -1;
+    for (char* q = bus; *q; q++) if (*q >= 'A' && *q <= 'Z') *q = (char)(*q - 'A' + 'a');
+    char path[160];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) return -1;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return -1;
+    cpu_set_t allowed, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) { fclose(f); return -1; }
+    int lo, hi, any = 0;
+    while (fscanf(f, "%d", &lo) == 1) {
+        hi = lo;
+        int ch = fgetc(f);
+        if (ch == '-') { if (fscanf(f, "%d", &hi) != 1) break; ch = fgetc(f); }
+        for (int k = lo; k <= hi && k < CPU_SETSIZE; k++) if (CPU_ISSET(k, &allowed)) { CPU_SET(k, &want); any = 1; }
+        if (ch != ',') break;
+    }
+    fclose(f);
+    if (!any) return -1;
+    if (sched_setaffinity(0, sizeof want, &want) != 0) return -1;
+    return node;
+}
+
+// Size the per-device pools of the host entry points ahead of time: waves of up to `wave_units` units,
+// `wave_in_bytes` input bytes and `wave_out_bytes` output bytes then run without any allocation.
+int sb_reserve(size_t wave_units, size_t wave_in_bytes, size_t wave_out_bytes, sb_error* err) {
+    Ctx* c;
+    int rc = get_ctx(&c, err);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int b = 0; b < 2; b++) {
+        CK(c->in[b].need(wave_in_bytes + wave_units * 16 + 64));
+        CK(c->slots[b].need(wave_units * (size_t)sbk::kSlotStride));
+        CK(c->compact[b].need(wave_out_bytes + wave_units * 16 + 64));
+        CK(c->lens[b].need(wave_units * 4 + 4));
+        CK(c->caps[b].need(wave_units * 8 + 8));
+        CK(c->status[b].need(wave_units * sizeof(sb_error) + 64));
+        CK(c->ptrs_in[b].need(wave_units * 8 + 8));
+        CK(c->ptrs_out[b].need(wave_units * 8 + 8));
+        CK(c->ws[b].need(align_up((wave_units / sbk::K4_TILE + 3) * 8, 256) + align_up((wave_units + 1) * 8, 256) + 1024));
+        rc = need_pinned(*c, b, wave_units * 24 + 64, err); if (rc) return rc;
+        rc = need_pinned(*c, 2 + b, wave_units * (4 + sizeof(sb_error)) + 64, err); if (rc) return rc;
+    }
+    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
+    ok(err);
+    return 0;
+}
+
+uint64_t sb_frame_encode_scratch_bytes(uint64_t n) { return encode_ws_bytes(n); }
+uint64_t sb_frame_decode_scratch_bytes(uint32_t max_chunks) { return decode_ws_bytes(max_chunks); }
+
 int sb_compress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_n, sb_error* err) {
     if ((!in && n) || !out || !out_n) return fail(err, SB_E_INVALID);
     const size_t need = sb_max_compress_len(n);
@@ -381,13 +458,19 @@ int sb_compress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* o
     std::lock_guard<std::mutex> lk(c->mu);
     CK(c->in[0].need(n + 64));
     CK(c->compact[0].need(need + 64));
+    CK(c->ws[0].need(encode_ws_bytes(n) + sizeof(sb_frame_result) + 256));
+    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
     if (n) CK(cudaMemcpyAsync(c->in[0].p, in, n, cudaMemcpyHostToDevice, c->s_compute));
-    uint64_t total = 0;
-    rc = compress_stream_device(*c, c->in[0].as<uint8_t>(), n, c->compact[0].as<uint8_t>(), 0, 0, &total, c->s_compute, err);
+    sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)c->ws[0].p + align_up(encode_ws_bytes(n), 256));
+    rc = compress_stream_ws(*c, c->in[0].as<uint8_t>(), n, c->compact[0].as<uint8_t>(), need, 0, 0, nullptr, d_res, c->ws[0].p, c->s_compute, err);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(out, c->compact[0].p, total, cudaMemcpyDeviceToHost, c->s_compute));
+    sb_frame_result* res = (sb_frame_result*)c->pinned[4];
+    CK(cudaMemcpyAsync(res, d_res, sizeof *res, cudaMemcpyDeviceToHost, c->s_compute));
     CK(cudaStreamSynchronize(c->s_compute));
-    *out_n = (size_t)total;
+    if (res->status.code) { if (err) *err = res->status; return (int)res->status.code; }
+    CK(cudaMemcpyAsync(out, c->compact[0].p, res->bytes, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    *out_n = (size_t)res->bytes;
     ok(err);
     return 0;
 }
@@ -420,6 +503,7 @@ int sb_decompress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t*
     CK(c->in[0].need(n + 64));
     CK(c->compact[0].need(dcap + 64));
     CK(c->status[0].need(sizeof(sb_error) + 16));
+    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
     CK(cudaMemcpyAsync(c->in[0].p, in, n, cudaMemcpyHostToDevice, c->s_compute));
     sb_batch b;
     memset(&b, 0, sizeof b);
@@ -431,12 +515,13 @@ int sb_decompress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t*
     b.count = 1;
     rc = launch_k2(*c, b, c->s_compute, err);
     if (rc) return rc;
-    struct { sb_error e; uint32_t len; uint32_t pad; } res;
-    CK(cudaMemcpyAsync(&res, c->status[0].p, sizeof(sb_error) + 8, cudaMemcpyDeviceToHost, c->s_compute));
+    struct Res { sb_error e; uint32_t len; uint32_t pad; };
+    Res* res = (Res*)c->pinned[4];
+    CK(cudaMemcpyAsync(res, c->status[0].p, sizeof(sb_error) + 8, cudaMemcpyDeviceToHost, c->s_compute));
     CK(cudaStreamSynchronize(c->s_compute));
-    if (res.e.code) { if (err) *err = res.e; return (int)res.e.code; }
-    if (res.len) CK(cudaMemcpy(out, c->compact[0].p, res.len, cudaMemcpyDeviceToHost));
-    *out_n = res.len;
+    if (res->e.code) { if (err) *err = res->e; return (int)res->e.code; }
+    if (res->len) CK(cudaMemcpy(out, c->compact[0].p, res->len, cudaMemcpyDeviceToHost));
+    *out_n = res->len;
     ok(err);
     return 0;
 }
@@ -448,15 +533,15 @@ int sb_crc32c_masked(const uint8_t* in, size_t n, uint32_t* out, sb_error* err) 
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     CK(c->in[0].need(n + 64));
-    CK(c->crcs[0].need(16));
+    CK(c->lens[0].need(16));
     if (n) CK(cudaMemcpyAsync(c->in[0].p, in, n, cudaMemcpyHostToDevice, c->s_compute));
     sb_batch b;
     memset(&b, 0, sizeof b);
     b.in_base = c->in[0].as<uint8_t>(); b.in_len_uniform = (uint32_t)n;
-    b.out_lens = c->crcs[0].as<uint32_t>(); b.count = 1;
+    b.out_lens = c->lens[0].as<uint32_t>(); b.count = 1;
     rc = launch_k3(*c, b, c->s_compute, err);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(out, c->crcs[0].p, 4, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaMemcpyAsync(out, c->lens[0].p, 4, cudaMemcpyDeviceToHost, c->s_compute));
     CK(cudaStreamSynchronize(c->s_compute));
     ok(err);
     return 0;
@@ -465,10 +550,13 @@ int sb_crc32c_masked(const uint8_t* in, size_t n, uint32_t* out, sb_error* err) 
 // ---------------------------------------------------------- device batches
 int sb_compress_batch_device(const sb_batch* batch, void* stream, sb_error* err) {
     if (!batch || !batch->out_lens) return fail(err, SB_E_INVALID);
+    if (!batch->in_lens && batch->in_len_uniform > SB_MAX_BLOCK) return fail(err, SB_TOO_BIG, batch->in_len_uniform, SB_MAX_BLOCK);
+    if (!batch->out_caps && !batch->in_lens && batch->out_cap_uniform < sb_max_compress_len(batch->in_len_uniform))
+        return fail(err, SB_BUFFER_TOO_SMALL, batch->out_cap_uniform, sb_max_compress_len(batch->in_len_uniform));
     Ctx* c;
     int rc = get_ctx(&c, err);
     if (rc) return rc;
-    rc = launch_k1(*c, *batch, 1u, (cudaStream_t)stream, err);
+    rc = launch_k1(*c, *batch, 1u, nullptr, (cudaStream_t)stream, err);
     if (rc) return rc;
     ok(err);
     return 0;
@@ -516,7 +604,8 @@ int sb_generate_blocks_device(const uint8_t* d_text, uint64_t text_len, uint8_t*
 
 // ------------------------------------------------------------ host batches
 // Waves of units are staged H2D on one stream, run on a second, and drained D2H
-// on a third, double buffered, so PCIe traffic overlaps the kernels.
+// on a third, double buffered, so PCIe traffic overlaps the kernels. The host thread
+// never waits for a copy: ordering between the streams is all events.
 namespace {
 const size_t WAVE_BYTES = (size_t)1 << 30;
 
@@ -539,29 +628,19 @@ std::vector<Wave> plan_waves(const uint32_t* in_lens, size_t count, const uint32
     }
     return w;
 }
-}  // namespace
 
-int sb_compress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, const uint32_t* in_lens,
-                           uint8_t* out_base, const uint64_t* out_offs, const uint32_t* out_caps,
-                           uint32_t* out_lens, size_t count, sb_error* err) {
-    if (!in_base || !in_offs || !in_lens || !out_base || !out_offs || !out_lens) return fail(err, SB_E_INVALID);
-    for (size_t i = 0; i < count; i++) {
-        if (in_lens[i] > SB_MAX_BLOCK) return fail(err, SB_E_INVALID, i);   // one block per unit in the batched form
-        if (out_caps && out_caps[i] < sb_max_compress_len(in_lens[i]))
-            return fail(err, SB_BUFFER_TOO_SMALL, out_caps[i], sb_max_compress_len(in_lens[i]));
-    }
+// Shared body of sb_compress_batch_host (caller's offsets) and sb_compress_batch_host_packed (the library packs the
+// streams back to back and REPORTS the offsets: a caller cannot know compressed sizes in advance).
+int compress_batch_host_impl(const uint8_t* in_base, const uint64_t* in_offs, const uint32_t* in_lens,
+                             uint8_t* out_base, const uint64_t* out_offs_in, uint64_t out_cap_total, uint64_t* out_offs_ret,
+                             uint32_t* out_lens, size_t count, sb_error* err) {
+    const bool packed = out_offs_in == nullptr;
     Ctx* c;
     int rc = get_ctx(&c, err);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     std::vector<Wave> waves = plan_waves(in_lens, count, nullptr);
-    cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
-    for (int k = 0; k < 2; k++) {
-        CK(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_k[k], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
-    }
-    std::vector<uint64_t> dev_in_off[2];
+    std::vector<uint64_t> doff;
     auto stage_in = [&](size_t wi) -> int {
         const Wave& w = waves[wi];
         const int b = (int)(wi & 1);
@@ -571,7 +650,6 @@ int sb_compress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, cons
         CK(c->caps[b].need(w.count * 4 + 4));
         CK(c->ptrs_in[b].need(w.count * 8 + 8));
         // coalesce units that are contiguous on the host into single copies
-        std::vector<uint64_t>& doff = dev_in_off[b];
         doff.resize(w.count);
         uint64_t at = 0;
         size_t i = 0;
@@ -584,6 +662,7 @@ int sb_compress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, cons
             at += (run + 15) & ~(uint64_t)15;
             i = j;
         }
+        // pinned[b] was last read by the H2D of wave wi-2, whose kernel has completed (the loop below waited for it)
         { int prc = need_pinned(*c, b, w.count * 12 + 64, err); if (prc) return prc; }
         uint64_t* ptrs = (uint64_t*)c->pinned[b];
         uint32_t* plen = (uint32_t*)(ptrs + w.count);
@@ -591,73 +670,101 @@ int sb_compress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, cons
         memcpy(plen, in_lens + w.first, w.count * 4);
         CK(cudaMemcpyAsync(c->ptrs_in[b].p, ptrs, w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
         CK(cudaMemcpyAsync(c->caps[b].p, plen, w.count * 4, cudaMemcpyHostToDevice, c->s_h2d));
-        CK(cudaStreamSynchronize(c->s_h2d));   // host temporaries + simple ordering; copies of the NEXT wave overlap kernels
-        CK(cudaEventRecord(ev_in[b], c->s_h2d));
+        CK(cudaEventRecord(c->ev_in[b], c->s_h2d));
         return 0;
     };
     const bool timing = getenv("SNAPB200_TIMING") != nullptr;
     auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t_begin = now_ms();
+    uint64_t packed_at = 0;
     if (!waves.empty()) { rc = stage_in(0); if (rc) return rc; }
     for (size_t wi = 0; wi < waves.size(); wi++) {
         const Wave& w = waves[wi];
         const int b = (int)(wi & 1);
         if (timing) fprintf(stderr, "[compress wave %zu] t=%.2f launch (count %zu)\n", wi, now_ms() - t_begin, w.count);
-        CK(cudaStreamWaitEvent(c->s_compute, ev_in[b], 0));
-        if (wi >= 2) CK(cudaStreamWaitEvent(c->s_compute, ev_out[b], 0));   // wave wi-2 (same buffers) fully drained
+        CK(cudaStreamWaitEvent(c->s_compute, c->ev_in[b], 0));
+        if (wi >= 2) CK(cudaStreamWaitEvent(c->s_compute, c->ev_out[b], 0));   // wave wi-2 (same buffers) fully drained
         sb_batch bt;
         memset(&bt, 0, sizeof bt);
         bt.in_ptrs = (const uint8_t* const*)c->ptrs_in[b].p; bt.in_lens = c->caps[b].as<uint32_t>();
         bt.out_base = c->slots[b].as<uint8_t>(); bt.out_stride = sbk::kSlotStride; bt.out_cap_uniform = sbk::kSlotStride;
         bt.out_lens = c->lens[b].as<uint32_t>(); bt.count = (uint32_t)w.count;
-        cudaEvent_t tk0 = nullptr, tk1 = nullptr;
-        if (timing) { cudaEventCreate(&tk0); cudaEventCreate(&tk1); cudaEventRecord(tk0, c->s_compute); }
-        rc = launch_k1(*c, bt, 1u, c->s_compute, err);
+        rc = launch_k1(*c, bt, 1u, nullptr, c->s_compute, err);
         if (rc) return rc;
-        if (timing) cudaEventRecord(tk1, c->s_compute);
+        // pack the wave's streams back to back on the device (offsets by scan), so the drain is one D2H
+        uint64_t worst = 0;
+        for (size_t k = 0; k < w.count; k++) worst += sb_max_compress_len(in_lens[w.first + k]);
+        CK(c->compact[b].need(worst + 64));
+        const size_t tiles_bytes = align_up((w.count / sbk::K4_TILE + 3) * 8, 256);
+        CK(c->ws[b].need(tiles_bytes + align_up((w.count + 1) * 8, 256) + 1024));
+        sbk::FramePlan p;
+        memset(&p, 0, sizeof p);
+        p.slots = c->slots[b].as<uint8_t>(); p.clens = c->lens[b].as<uint32_t>(); p.nchunks = (uint32_t)w.count;
+        p.frame = 0; p.head_len = 0; p.tiles = (uint64_t*)c->ws[b].p; p.offs = (uint64_t*)((uint8_t*)c->ws[b].p + tiles_bytes);
+        p.out = c->compact[b].as<uint8_t>(); p.cap = c->compact[b].cap; p.result = nullptr;
+        rc = launch_assemble(*c, p, c->s_compute, err);
+        if (rc) return rc;
         // results come back through pinned staging: a D2H copy into the caller's (pageable) array
         // would block this thread until the kernel is done and serialise the next wave's H2D behind it
-        { int prc = need_pinned(*c, 2 + b, w.count * 4 + 64, err); if (prc) return prc; }
-        CK(cudaMemcpyAsync(c->pinned[2 + b], c->lens[b].p, w.count * 4, cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaEventRecord(ev_k[b], c->s_compute));
+        { int prc = need_pinned(*c, 2 + b, w.count * 12 + 64, err); if (prc) return prc; }
+        uint32_t* plens = (uint32_t*)c->pinned[2 + b];
+        uint64_t* poffs = (uint64_t*)(plens + ((w.count + 2) & ~(size_t)1));
+        CK(cudaMemcpyAsync(plens, c->lens[b].p, w.count * 4, cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaMemcpyAsync(poffs, p.offs, (w.count + 1) * 8, cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaEventRecord(c->ev_k[b], c->s_compute));
         if (wi + 1 < waves.size()) { rc = stage_in(wi + 1); if (rc) return rc; }   // overlaps the kernel above
         if (timing) fprintf(stderr, "[compress wave %zu] t=%.2f staged next\n", wi, now_ms() - t_begin);
-        CK(cudaEventSynchronize(ev_k[b]));
-        memcpy(out_lens + w.first, c->pinned[2 + b], w.count * 4);
-        if (timing) { float kms = 0; cudaEventElapsedTime(&kms, tk0, tk1); fprintf(stderr, "[compress wave %zu] t=%.2f kernel done (kernel %.2f ms)\n", wi, now_ms() - t_begin, kms); cudaEventDestroy(tk0); cudaEventDestroy(tk1); }
-        // drain: contiguous host destinations are gathered on the device first, then one D2H
-        bool dense = true;
-        uint64_t run = 0;
-        for (size_t k = 0; k < w.count && dense; k++) {
-            if (out_offs[w.first + k] != out_offs[w.first] + run) dense = false;
-            run += out_lens[w.first + k];
-        }
-        if (dense && w.count > 1) {
-            CK(c->compact[b].need(run + 64));
-            CK(c->csize[b].need(w.count * 4 + 4));
-            CK(c->offs[b].need((w.count + 1) * 8));
-            sbk::FramePlan p;
-            memset(&p, 0, sizeof p);
-            p.slots = c->slots[b].as<uint8_t>(); p.clens = c->lens[b].as<uint32_t>(); p.nchunks = (uint32_t)w.count;
-            p.frame = 0; p.base = 0; p.csize = c->csize[b].as<uint32_t>(); p.offs = c->offs[b].as<uint64_t>();
-            p.out = c->compact[b].as<uint8_t>();
-            rc = launch_assemble(*c, p, c->s_compute, err);
-            if (rc) return rc;
-            CK(cudaEventRecord(ev_k[b], c->s_compute));
-            CK(cudaStreamWaitEvent(c->s_d2h, ev_k[b], 0));
-            CK(cudaMemcpyAsync(out_base + out_offs[w.first], c->compact[b].p, run, cudaMemcpyDeviceToHost, c->s_d2h));
+        CK(cudaEventSynchronize(c->ev_k[b]));
+        memcpy(out_lens + w.first, plens, w.count * 4);
+        const uint64_t run = poffs[w.count];
+        if (timing) fprintf(stderr, "[compress wave %zu] t=%.2f kernel done (%llu bytes)\n", wi, now_ms() - t_begin, (unsigned long long)run);
+        CK(cudaStreamWaitEvent(c->s_d2h, c->ev_k[b], 0));
+        if (packed) {
+            if (packed_at + run > out_cap_total) return fail(err, SB_BUFFER_TOO_SMALL, out_cap_total, packed_at + run);
+            for (size_t k = 0; k < w.count; k++) out_offs_ret[w.first + k] = packed_at + poffs[k];
+            if (run) CK(cudaMemcpyAsync(out_base + packed_at, c->compact[b].p, run, cudaMemcpyDeviceToHost, c->s_d2h));
+            packed_at += run;
         } else {
-            for (size_t k = 0; k < w.count; k++)
-                CK(cudaMemcpyAsync(out_base + out_offs[w.first + k], c->slots[b].as<uint8_t>() + k * (size_t)sbk::kSlotStride,
-                                   out_lens[w.first + k], cudaMemcpyDeviceToHost, c->s_d2h));
+            // caller's offsets: host-contiguous destinations travel as one copy per run
+            size_t k = 0;
+            while (k < w.count) {
+                size_t j = k;
+                uint64_t len = 0;
+                const uint64_t h0 = out_offs_in[w.first + k];
+                while (j < w.count && out_offs_in[w.first + j] == h0 + len) { len += plens[j]; j++; }
+                if (len) CK(cudaMemcpyAsync(out_base + h0, c->compact[b].as<uint8_t>() + poffs[k], len, cudaMemcpyDeviceToHost, c->s_d2h));
+                k = j;
+            }
         }
-        CK(cudaEventRecord(ev_out[b], c->s_d2h));
+        CK(cudaEventRecord(c->ev_out[b], c->s_d2h));
     }
+    if (packed) out_offs_ret[count] = packed_at;
     CK(cudaStreamSynchronize(c->s_d2h));
     CK(cudaStreamSynchronize(c->s_compute));
-    for (int k = 0; k < 2; k++) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_k[k]); cudaEventDestroy(ev_out[k]); }
     ok(err);
     return 0;
+}
+}  // namespace
+
+int sb_compress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, const uint32_t* in_lens,
+                           uint8_t* out_base, const uint64_t* out_offs, const uint32_t* out_caps,
+                           uint32_t* out_lens, size_t count, sb_error* err) {
+    if (!in_base || !in_offs || !in_lens || !out_base || !out_offs || !out_lens) return fail(err, SB_E_INVALID);
+    for (size_t i = 0; i < count; i++) {
+        if (in_lens[i] > SB_MAX_BLOCK) return fail(err, SB_TOO_BIG, in_lens[i], SB_MAX_BLOCK);   // one block per unit in the batched form
+        if (out_caps && out_caps[i] < sb_max_compress_len(in_lens[i]))
+            return fail(err, SB_BUFFER_TOO_SMALL, out_caps[i], sb_max_compress_len(in_lens[i]));
+    }
+    return compress_batch_host_impl(in_base, in_offs, in_lens, out_base, out_offs, 0, nullptr, out_lens, count, err);
+}
+
+int sb_compress_batch_host_packed(const uint8_t* in_base, const uint64_t* in_offs, const uint32_t* in_lens,
+                                  uint8_t* out_base, uint64_t out_cap, uint64_t* out_offs, uint32_t* out_lens,
+                                  size_t count, sb_error* err) {
+    if (!in_base || !in_offs || !in_lens || !out_base || !out_offs || !out_lens) return fail(err, SB_E_INVALID);
+    for (size_t i = 0; i < count; i++)
+        if (in_lens[i] > SB_MAX_BLOCK) return fail(err, SB_TOO_BIG, in_lens[i], SB_MAX_BLOCK);
+    return compress_batch_host_impl(in_base, in_offs, in_lens, out_base, nullptr, out_cap, out_offs, out_lens, count, err);
 }
 
 int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, const uint32_t* in_lens,
@@ -670,13 +777,7 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     std::vector<Wave> waves = plan_waves(in_lens, count, out_caps);
-    cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
-    for (int k = 0; k < 2; k++) {
-        CK(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_k[k], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
-    }
-    std::vector<uint64_t> pin[2], pout[2];
+    std::vector<uint64_t> pout[2];
     // H2D of wave wi into buffer set wi&1 (copy stream; overlaps the previous wave's kernel)
     auto stage_in = [&](size_t wi) -> int {
         const Wave& w = waves[wi];
@@ -690,7 +791,9 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
         CK(c->status[b].need(w.count * sizeof(sb_error)));
         CK(c->ptrs_in[b].need(w.count * 8 + 8));
         CK(c->ptrs_out[b].need(w.count * 8 + 8));
-        pin[b].resize(w.count); pout[b].resize(w.count);
+        { int prc = need_pinned(*c, b, w.count * 24 + 64, err); if (prc) return prc; }
+        uint64_t* sp = (uint64_t*)c->pinned[b];      // [count] in pointers, [count] out pointers, then lengths and caps
+        pout[b].resize(w.count);
         uint64_t at = 0, oat = 0;
         size_t i = 0;
         while (i < w.count) {                                      // host-contiguous units travel as one copy
@@ -698,7 +801,7 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
             uint64_t run = 0;
             const uint64_t h0 = in_offs[w.first + i];
             while (j < w.count && in_offs[w.first + j] == h0 + run) {
-                pin[b][j] = (uint64_t)(uintptr_t)(c->in[b].as<uint8_t>() + at + run); run += in_lens[w.first + j]; j++;
+                sp[j] = (uint64_t)(uintptr_t)(c->in[b].as<uint8_t>() + at + run); run += in_lens[w.first + j]; j++;
             }
             if (run) CK(cudaMemcpyAsync(c->in[b].as<uint8_t>() + at, in_base + h0, run, cudaMemcpyHostToDevice, c->s_h2d));
             at += (run + 15) & ~(uint64_t)15;
@@ -706,28 +809,24 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
         }
         for (size_t k = 0; k < w.count; k++) {
             pout[b][k] = (uint64_t)(uintptr_t)(c->compact[b].as<uint8_t>() + oat);
+            sp[w.count + k] = pout[b][k];
             oat += ((uint64_t)out_caps[w.first + k] + 15) & ~(uint64_t)15;
         }
-        { int prc = need_pinned(*c, b, w.count * 24 + 64, err); if (prc) return prc; }
-        uint64_t* sp = (uint64_t*)c->pinned[b];
-        memcpy(sp, pin[b].data(), w.count * 8);
-        memcpy(sp + w.count, pout[b].data(), w.count * 8);
         uint32_t* sl = (uint32_t*)(sp + 2 * w.count);
         memcpy(sl, in_lens + w.first, w.count * 4);
         memcpy(sl + w.count, out_caps + w.first, w.count * 4);
         CK(cudaMemcpyAsync(c->ptrs_in[b].p, sp, w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
         CK(cudaMemcpyAsync(c->ptrs_out[b].p, sp + w.count, w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
         CK(cudaMemcpyAsync(c->caps[b].p, sl, w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
-        CK(cudaStreamSynchronize(c->s_h2d));
-        CK(cudaEventRecord(ev_in[b], c->s_h2d));
+        CK(cudaEventRecord(c->ev_in[b], c->s_h2d));
         return 0;
     };
     if (!waves.empty()) { rc = stage_in(0); if (rc) return rc; }
     for (size_t wi = 0; wi < waves.size(); wi++) {
         const Wave& w = waves[wi];
         const int b = (int)(wi & 1);
-        CK(cudaStreamWaitEvent(c->s_compute, ev_in[b], 0));
-        if (wi >= 2) CK(cudaStreamWaitEvent(c->s_compute, ev_out[b], 0));   // wave wi-2 (same buffers) fully drained
+        CK(cudaStreamWaitEvent(c->s_compute, c->ev_in[b], 0));
+        if (wi >= 2) CK(cudaStreamWaitEvent(c->s_compute, c->ev_out[b], 0));   // wave wi-2 (same buffers) fully drained
         sb_batch bt;
         memset(&bt, 0, sizeof bt);
         bt.in_ptrs = (const uint8_t* const*)c->ptrs_in[b].p; bt.in_lens = c->caps[b].as<uint32_t>();
@@ -740,12 +839,14 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
         uint32_t* pln = (uint32_t*)(pst + w.count);
         CK(cudaMemcpyAsync(pln, c->lens[b].p, w.count * 4, cudaMemcpyDeviceToHost, c->s_compute));
         CK(cudaMemcpyAsync(pst, c->status[b].p, w.count * sizeof(sb_error), cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaEventRecord(ev_k[b], c->s_compute));
+        CK(cudaEventRecord(c->ev_k[b], c->s_compute));
+        // the next wave's staging writes pout[b^1] only: this wave's pout[b] stays valid for the drain below
         if (wi + 1 < waves.size()) { rc = stage_in(wi + 1); if (rc) return rc; }   // overlaps the kernel above and the previous drain
-        CK(cudaEventSynchronize(ev_k[b]));
+        CK(cudaEventSynchronize(c->ev_k[b]));
         memcpy(out_lens + w.first, pln, w.count * 4);
         memcpy(statuses + w.first, pst, w.count * sizeof(sb_error));
         // drain on the third stream; contiguous destinations whose caps are exactly filled go out as one copy
+        CK(cudaStreamWaitEvent(c->s_d2h, c->ev_k[b], 0));
         const uint64_t cbase = (uint64_t)(uintptr_t)c->compact[b].p;
         size_t k = 0;
         while (k < w.count) {
@@ -762,16 +863,31 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
             if (run) CK(cudaMemcpyAsync(out_base + h0, c->compact[b].as<uint8_t>() + d0, run, cudaMemcpyDeviceToHost, c->s_d2h));
             k = j;
         }
-        CK(cudaEventRecord(ev_out[b], c->s_d2h));
+        CK(cudaEventRecord(c->ev_out[b], c->s_d2h));
     }
     CK(cudaStreamSynchronize(c->s_d2h));
     CK(cudaStreamSynchronize(c->s_compute));
-    for (int k = 0; k < 2; k++) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_k[k]); cudaEventDestroy(ev_out[k]); }
     ok(err);
     return 0;
 }
 
 // -------------------------------------------------------------- frame format
+// Stream-ordered, caller-provided scratch, no allocation, no host synchronisation (n > 0).
+int sb_frame_encode_device_ws(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap, int include_ident,
+                              uint64_t* d_chunk_offs, sb_frame_result* d_result, void* scratch, uint64_t scratch_bytes,
+                              void* stream, sb_error* err) {
+    if ((!d_in && n) || (!d_out && n) || !d_result || (!scratch && n)) return fail(err, SB_E_INVALID);
+    if (scratch_bytes < encode_ws_bytes(n)) return fail(err, SB_BUFFER_TOO_SMALL, scratch_bytes, encode_ws_bytes(n));
+    Ctx* c;
+    int rc = get_ctx(&c, err);
+    if (rc) return rc;
+    rc = compress_stream_ws(*c, d_in, n, d_out, cap, 1, include_ident, d_chunk_offs, d_result, scratch,
+                            stream ? (cudaStream_t)stream : c->s_compute, err);
+    if (rc) return rc;
+    ok(err);
+    return 0;
+}
+
 int sb_frame_encode_device(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap,
                            int include_ident, uint64_t* out_n, void* stream, sb_error* err) {
     if ((!d_in && n) || !out_n || (!d_out && n)) return fail(err, SB_E_INVALID);
@@ -780,8 +896,17 @@ int sb_frame_encode_device(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint
     int rc = get_ctx(&c, err);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
-    rc = compress_stream_device(*c, d_in, n, d_out, 1, include_ident, out_n, stream ? (cudaStream_t)stream : c->s_compute, err);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    CK(c->ws[0].need(encode_ws_bytes(n) + sizeof(sb_frame_result) + 256));
+    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
+    sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)c->ws[0].p + align_up(encode_ws_bytes(n), 256));
+    rc = compress_stream_ws(*c, d_in, n, d_out, cap, 1, include_ident, nullptr, d_res, c->ws[0].p, st, err);
     if (rc) return rc;
+    sb_frame_result* res = (sb_frame_result*)c->pinned[4];
+    CK(cudaMemcpyAsync(res, d_res, sizeof *res, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (res->status.code) { if (err) *err = res->status; return (int)res->status.code; }
+    *out_n = res->bytes;
     ok(err);
     return 0;
 }
@@ -800,178 +925,121 @@ int sb_frame_encode_ex(const uint8_t* in, size_t n, uint8_t* out, size_t cap, si
     std::lock_guard<std::mutex> lk(c->mu);
     CK(c->in[1].need(n + 64));
     CK(c->compact[1].need(sb_frame_max_len(n) + 64));
+    CK(c->ws[1].need(encode_ws_bytes(n) + sizeof(sb_frame_result) + 256));
+    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
     CK(cudaMemcpyAsync(c->in[1].p, in, n, cudaMemcpyHostToDevice, c->s_compute));
-    uint64_t total = 0;
-    rc = compress_stream_device(*c, c->in[1].as<uint8_t>(), n, c->compact[1].as<uint8_t>(), 1, include_ident, &total, c->s_compute, err);
+    sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)c->ws[1].p + align_up(encode_ws_bytes(n), 256));
+    rc = compress_stream_ws(*c, c->in[1].as<uint8_t>(), n, c->compact[1].as<uint8_t>(), sb_frame_max_len(n), 1, include_ident,
+                            nullptr, d_res, c->ws[1].p, c->s_compute, err);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(out, c->compact[1].p, total, cudaMemcpyDeviceToHost, c->s_compute));
+    sb_frame_result* res = (sb_frame_result*)c->pinned[4];
+    CK(cudaMemcpyAsync(res, d_res, sizeof *res, cudaMemcpyDeviceToHost, c->s_compute));
     CK(cudaStreamSynchronize(c->s_compute));
-    *out_n = (size_t)total;
+    if (res->status.code) { if (err) *err = res->status; return (int)res->status.code; }
+    CK(cudaMemcpyAsync(out, c->compact[1].p, res->bytes, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    *out_n = (size_t)res->bytes;
     ok(err);
     return 0;
 }
 
-// read::FrameDecoder + read_to_end over host memory (reference src/read.rs:104-239).
-// The host walks the chunk headers (each one gives the next offset), the device
-// decodes every compressed chunk (K2), copies uncompressed ones, checksums all
-// outputs (K3); the first failure IN STREAM ORDER is reported.
+// Device-resident frame decode, stream ordered, caller-provided scratch (reference src/read.rs:104-239).
+//   d_chunk_offs/nchunks: optional index (offset of every chunk header, d_chunk_offs[nchunks] = n) -- the array
+//     sb_frame_encode_device_ws emits; without it one thread walks the headers (~1 us per chunk).
+//   flags bit0: the stream has no identifier (a rank's fragment of a sharded stream).
+int sb_frame_decode_device_ws(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap,
+                              const uint64_t* d_chunk_offs, uint32_t nchunks, uint32_t flags,
+                              sb_frame_result* d_result, void* scratch, uint64_t scratch_bytes, uint32_t max_chunks,
+                              void* stream, sb_error* err) {
+    if ((!d_in && n) || (!d_out && cap) || !d_result || !scratch || max_chunks == 0) return fail(err, SB_E_INVALID);
+    if (d_chunk_offs && nchunks > max_chunks) return fail(err, SB_E_INVALID, nchunks, max_chunks);
+    if (scratch_bytes < decode_ws_bytes(max_chunks)) return fail(err, SB_BUFFER_TOO_SMALL, scratch_bytes, decode_ws_bytes(max_chunks));
+    Ctx* c;
+    int rc = get_ctx(&c, err);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    const sbk::DecodePlan p = make_decode_plan(d_in, n, d_out, cap, d_chunk_offs, nchunks, (int)(flags & 1u), d_result, scratch, max_chunks);
+    rc = decode_index_phase(*c, p, st, err);
+    if (rc) return rc;
+    rc = decode_payload_phase(*c, p, st, err);
+    if (rc) return rc;
+    ok(err);
+    return 0;
+}
+
+// Convenience form: pooled scratch, waits for the result (host sb_frame_result).
+int sb_frame_decode_device(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint64_t cap,
+                           const uint64_t* d_chunk_offs, uint32_t nchunks, uint32_t flags,
+                           sb_frame_result* result, void* stream, sb_error* err) {
+    if (!result) return fail(err, SB_E_INVALID);
+    Ctx* c;
+    int rc = get_ctx(&c, err);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    uint64_t maxc = d_chunk_offs ? (uint64_t)nchunks + 1 : n / 1024 + 4096;
+    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
+    for (;;) {
+        if (maxc > 0xFFFFFFF0ull) return fail(err, SB_E_INVALID);
+        CK(c->ws[1].need(decode_ws_bytes(maxc) + sizeof(sb_frame_result) + 256));
+        sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)c->ws[1].p + align_up(decode_ws_bytes(maxc), 256));
+        sb_error e2;
+        rc = sb_frame_decode_device_ws(d_in, n, d_out, cap, d_chunk_offs, nchunks, flags, d_res, c->ws[1].p, decode_ws_bytes(maxc),
+                                       (uint32_t)maxc, st, &e2);
+        if (rc) { if (err) *err = e2; return rc; }
+        sb_frame_result* res = (sb_frame_result*)c->pinned[4];
+        CK(cudaMemcpyAsync(res, d_res, sizeof *res, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (res->status.code == SB_E_INVALID && res->status.b == 1 && maxc < n / 8 + 16) { maxc = maxc * 8; continue; }   // chunk table too small
+        *result = *res;
+        break;
+    }
+    ok(err);
+    return 0;
+}
+
+// read::FrameDecoder + read_to_end over host memory (reference src/read.rs:104-239): the stream is uploaded once
+// and decoded by the device path above (header walk, K2, checksum); the first failure IN STREAM ORDER is reported
+// and the bytes produced before it are returned, like a reader that fails on its n-th read.
 int sb_frame_decode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_n, sb_error* err) {
     if ((!in && n) || !out_n) return fail(err, SB_E_INVALID);
-    struct Chunk { uint64_t body_off; uint32_t body_len; uint32_t dlen; uint32_t want_crc; uint8_t type; };
-    std::vector<Chunk> chunks;
-    // shadow of the decoder's persistent 76490-byte `src` buffer, needed only for the
-    // reference quirk that decompress_len() is applied to the WHOLE buffer (src/read.rs:216)
-    std::vector<uint8_t> shadow(SB_MAX_CBLOCK, 0);
-    sb_error walk_err;
-    memset(&walk_err, 0, sizeof walk_err);
-    size_t pos = 0;
-    uint64_t produced = 0;
-    bool seen_ident = false;
-    auto werr = [&](uint32_t code, uint64_t a = 0, uint64_t b = 0) { walk_err.code = code; walk_err.a = a; walk_err.b = b; };
-    while (pos < n) {
-        if (n - pos < 4) { werr(SB_IO_UNEXPECTED_EOF); break; }
-        const uint8_t* h = in + pos;
-        memcpy(shadow.data(), h, 4);
-        pos += 4;
-        const uint8_t ty = h[0];
-        if (!seen_ident) {
-            if (ty != 0xFF) { werr(SB_STREAM_HEADER, ty); break; }
-            seen_ident = true;
-        }
-        const uint64_t len = (uint64_t)h[1] | ((uint64_t)h[2] << 8) | ((uint64_t)h[3] << 16);
-        if (len > SB_MAX_CBLOCK) { werr(SB_UNSUPPORTED_CHUNK_LENGTH, len, 0); break; }
-        if (ty >= 0x02 && ty <= 0x7F) { werr(SB_UNSUPPORTED_CHUNK_TYPE, ty); break; }
-        if ((ty >= 0x80 && ty <= 0xFD) || ty == 0xFE) {
-            if (n - pos < len) { werr(SB_IO_UNEXPECTED_EOF); break; }
-            memcpy(shadow.data(), in + pos, len);
-            pos += len;
-        } else if (ty == 0xFF) {
-            if (len != 6) { werr(SB_UNSUPPORTED_CHUNK_LENGTH, len, 1); break; }
-            if (n - pos < 6) { werr(SB_IO_UNEXPECTED_EOF); break; }
-            memcpy(shadow.data(), in + pos, 6);
-            if (memcmp(in + pos, "sNaPpY", 6) != 0) {
-                uint64_t a = 0;
-                for (int i = 0; i < 6; i++) a |= (uint64_t)in[pos + i] << (8 * i);
-                werr(SB_STREAM_HEADER_MISMATCH, a);
-                break;
-            }
-            pos += 6;
-        } else {
-            if (len < 4) { werr(SB_UNSUPPORTED_CHUNK_LENGTH, len, 0); break; }
-            if (n - pos < 4) { werr(SB_IO_UNEXPECTED_EOF); break; }
-            uint32_t want;
-            memcpy(&want, in + pos, 4);
-            pos += 4;
-            const uint32_t body = (uint32_t)len - 4;
-            Chunk ch{pos, body, 0, want, ty};
-            if (ty == 0x01) {
-                if (body > SB_MAX_BLOCK) { werr(SB_UNSUPPORTED_CHUNK_LENGTH, body, 0); break; }
-                if (n - pos < body) { werr(SB_IO_UNEXPECTED_EOF); break; }
-                ch.dlen = body;
-            } else {
-                if (n - pos < body) { werr(SB_IO_UNEXPECTED_EOF); break; }
-                // decompress_len over the persistent buffer: only the first <=10 bytes matter
-                uint8_t head[16];
-                const size_t fresh = body < 16 ? body : 16;
-                memcpy(head, in + pos, fresh);
-                if (fresh < 16) memcpy(head + fresh, shadow.data() + fresh, 16 - fresh);
-                uint64_t v = 0;
-                const size_t hl = get_varint(head, 16, &v);   // a varint never needs more than 10 bytes
-                if (hl == 0) { werr(SB_HEADER); break; }
-                if (v > SB_MAX_INPUT) { werr(SB_TOO_BIG, v, SB_MAX_INPUT); break; }
-                if (v > SB_MAX_BLOCK) { werr(SB_UNSUPPORTED_CHUNK_LENGTH, v, 0); break; }
-                ch.dlen = (uint32_t)v;
-                const size_t keep = body < 16 ? body : 16;   // later quirk reads only look at the first bytes
-                memcpy(shadow.data(), in + pos, keep);
-            }
-            pos += body;
-            chunks.push_back(ch);
-            produced += ch.dlen;
-        }
+    if (n == 0) { *out_n = 0; ok(err); return 0; }
+    Ctx* c;
+    int rc = get_ctx(&c, err);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = c->s_compute;
+    CK(c->in[1].need(n + 64));
+    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
+    CK(cudaMemcpyAsync(c->in[1].p, in, n, cudaMemcpyHostToDevice, st));
+    uint64_t maxc = n / 1024 + 4096;
+    sbk::DecodeCtl* hc = (sbk::DecodeCtl*)c->pinned[4];
+    sbk::DecodePlan p;
+    for (;;) {
+        CK(c->ws[1].need(decode_ws_bytes(maxc) + sizeof(sb_frame_result) + 256));
+        sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)c->ws[1].p + align_up(decode_ws_bytes(maxc), 256));
+        p = make_decode_plan(c->in[1].as<uint8_t>(), n, nullptr, out ? cap : ~0ull, nullptr, 0, 0, d_res, c->ws[1].p, (uint32_t)maxc);
+        rc = decode_index_phase(*c, p, st, err);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(hc, p.ctl, sizeof(sbk::DecodeCtl), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (hc->walk_err.code == SB_E_INVALID && hc->walk_err.b == 1 && maxc < n / 8 + 16) { maxc *= 8; continue; }
+        break;
     }
+    const uint64_t produced = hc->produced;
     // Sizing call: only possible failures that precede any data check are reported by the full call.
     if (!out) { *out_n = (size_t)produced; ok(err); return 0; }
     if (produced > cap) return fail(err, SB_BUFFER_TOO_SMALL, cap, produced);
-
-    uint64_t good = 0;      // bytes produced by chunks before the first failing chunk
-    sb_error first;
-    memset(&first, 0, sizeof first);
-    if (!chunks.empty()) {
-        Ctx* c;
-        int rc = get_ctx(&c, err);
-        if (rc) return rc;
-        std::lock_guard<std::mutex> lk(c->mu);
-        const size_t m = chunks.size();
-        CK(c->in[1].need(n + 64));
-        CK(c->compact[1].need(produced + 64));
-        CK(c->ptrs_in[1].need(m * 8 + 8));
-        CK(c->ptrs_out[1].need(m * 8 + 8));
-        CK(c->caps[1].need(m * 8 + 8));
-        CK(c->lens[1].need(m * 4 + 4));
-        CK(c->crcs[1].need(m * 4 + 4));
-        CK(c->status[1].need(m * sizeof(sb_error)));
-        CK(cudaMemcpyAsync(c->in[1].p, in, n, cudaMemcpyHostToDevice, c->s_compute));
-        // compressed chunks first, then uncompressed ones (two sub-batches sharing the arrays)
-        std::vector<uint64_t> pin(m), pout(m);
-        std::vector<uint32_t> ilen(m), ocap(m);
-        std::vector<size_t> order;
-        order.reserve(m);
-        for (size_t i = 0; i < m; i++) if (chunks[i].type == 0x00) order.push_back(i);
-        const size_t ncomp = order.size();
-        for (size_t i = 0; i < m; i++) if (chunks[i].type == 0x01) order.push_back(i);
-        std::vector<uint64_t> ooff(m);
-        uint64_t at = 0;
-        for (size_t i = 0; i < m; i++) { ooff[i] = at; at += chunks[i].dlen; }
-        for (size_t k = 0; k < m; k++) {
-            const Chunk& ch = chunks[order[k]];
-            pin[k] = (uint64_t)(uintptr_t)(c->in[1].as<uint8_t>() + ch.body_off);
-            pout[k] = (uint64_t)(uintptr_t)(c->compact[1].as<uint8_t>() + ooff[order[k]]);
-            ilen[k] = ch.body_len;
-            ocap[k] = ch.dlen;
-        }
-        CK(cudaMemcpyAsync(c->ptrs_in[1].p, pin.data(), m * 8, cudaMemcpyHostToDevice, c->s_compute));
-        CK(cudaMemcpyAsync(c->ptrs_out[1].p, pout.data(), m * 8, cudaMemcpyHostToDevice, c->s_compute));
-        CK(cudaMemcpyAsync(c->caps[1].p, ilen.data(), m * 4, cudaMemcpyHostToDevice, c->s_compute));
-        CK(cudaMemcpyAsync(c->caps[1].as<uint32_t>() + m, ocap.data(), m * 4, cudaMemcpyHostToDevice, c->s_compute));
-        CK(cudaMemsetAsync(c->status[1].p, 0, m * sizeof(sb_error), c->s_compute));
-        sb_batch bt;
-        memset(&bt, 0, sizeof bt);
-        bt.in_ptrs = (const uint8_t* const*)c->ptrs_in[1].p; bt.in_lens = c->caps[1].as<uint32_t>();
-        bt.out_ptrs = (uint8_t* const*)c->ptrs_out[1].p; bt.out_caps = c->caps[1].as<uint32_t>() + m;
-        bt.out_lens = c->lens[1].as<uint32_t>(); bt.statuses = c->status[1].as<sb_error>(); bt.count = (uint32_t)ncomp;
-        rc = launch_k2(*c, bt, c->s_compute, err);
-        if (rc) return rc;
-        sb_batch cp = bt;
-        cp.in_ptrs += ncomp; cp.in_lens += ncomp; cp.out_ptrs += ncomp; cp.out_caps += ncomp;
-        cp.out_lens = nullptr; cp.statuses = nullptr; cp.count = (uint32_t)(m - ncomp);
-        rc = launch_copy_units(*c, cp, c->s_compute, err);
-        if (rc) return rc;
-        // checksum every produced chunk: unit k = output of order[k], length dlen
-        sb_batch cr;
-        memset(&cr, 0, sizeof cr);
-        cr.in_ptrs = (const uint8_t* const*)c->ptrs_out[1].p; cr.in_lens = c->caps[1].as<uint32_t>() + m;
-        cr.out_lens = c->crcs[1].as<uint32_t>(); cr.count = (uint32_t)m;
-        rc = launch_k3(*c, cr, c->s_compute, err);
-        if (rc) return rc;
-        std::vector<sb_error> st(m);
-        std::vector<uint32_t> crc(m);
-        CK(cudaMemcpyAsync(st.data(), c->status[1].p, m * sizeof(sb_error), cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaMemcpyAsync(crc.data(), c->crcs[1].p, m * 4, cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaStreamSynchronize(c->s_compute));
-        std::vector<sb_error> by_chunk(m);
-        for (size_t k = 0; k < m; k++) {
-            sb_error e = st[k];
-            if (k >= ncomp) memset(&e, 0, sizeof e);
-            if (!e.code && crc[k] != chunks[order[k]].want_crc) { e.code = SB_CHECKSUM; e.a = chunks[order[k]].want_crc; e.b = crc[k]; }
-            by_chunk[order[k]] = e;
-        }
-        good = produced;
-        for (size_t i = 0; i < m; i++) if (by_chunk[i].code) { first = by_chunk[i]; good = ooff[i]; break; }
-        if (good) CK(cudaMemcpy(out, c->compact[1].p, good, cudaMemcpyDeviceToHost));
-    }
-    *out_n = (size_t)good;
-    if (first.code) { if (err) *err = first; return (int)first.code; }
-    if (walk_err.code) { if (err) *err = walk_err; return (int)walk_err.code; }
+    CK(c->compact[1].need(produced + 64));
+    p.out = c->compact[1].as<uint8_t>();
+    rc = decode_payload_phase(*c, p, st, err);
+    if (rc) return rc;
+    sb_frame_result* res = (sb_frame_result*)((uint8_t*)c->pinned[4] + 512);
+    CK(cudaMemcpyAsync(res, p.result, sizeof *res, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (res->bytes) CK(cudaMemcpy(out, c->compact[1].p, res->bytes, cudaMemcpyDeviceToHost));
+    *out_n = (size_t)res->bytes;
+    if (res->status.code) { if (err) *err = res->status; return (int)res->status.code; }
     ok(err);
     return 0;
 }

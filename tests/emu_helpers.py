@@ -54,24 +54,35 @@ def _pack(chunks, slack=64):
     return buf, offs
 
 
-def compress_units(units, with_header=True, grid=1, global_window=False, parsers=1, multi=False, hybrid=False, mbar=False, gt_spec=False, w64=False, w64_aligned=False, unaligned=False, w64_gt=False, chains=0, exact=False):
-    """Run the K1 kernel body under the emulator over independent units (<=64KB each)."""
+def compress_units(units, with_header=True, grid=1, hybrid=False, chains=0, out_cap=None, statuses=False, crcs=False):
+    """Run the K1 kernel body under the emulator over independent units (<=64KB each).
+    hybrid: 7 shared-memory-table chains + 4 chains with tables in global memory (else 7 + 0)."""
     inbuf, inoffs = _pack(units, slack=3)
     stride = 76544
     out = np.full(stride * len(units) + 64, 0xEE, dtype=np.uint8)
     lens = np.array([len(u) for u in units], dtype=np.uint32)
     in_ptrs = np.array([inbuf.ctypes.data + o for o in inoffs], dtype=np.uint64)
     out_lens = np.zeros(len(units), dtype=np.uint32)
+    st = (SbError * len(units))()
     b = SbBatch()
     b.in_ptrs = in_ptrs.ctypes.data
     b.in_lens = lens.ctypes.data
     b.out_base = out.ctypes.data
     b.out_stride = stride
-    b.out_cap_uniform = stride
+    b.out_cap_uniform = stride if out_cap is None else out_cap
     b.out_lens = out_lens.ctypes.data
+    if statuses:
+        b.statuses = C.addressof(st)
     b.count = len(units)
-    lib().emu_compress_batch(C.byref(b), (1 if with_header else 0) | (0x100 if global_window else 0) | (parsers << 12) | (0x200 if multi else 0) | (0x400 if hybrid else 0) | (0x800 if mbar else 0) | (0x8000 if gt_spec else 0) | (0x10000 if w64 else 0) | (0x20000 if w64_aligned else 0) | (0x40000 if unaligned else 0) | (0x80000 if w64_gt else 0) | (chains << 20) | (0x1000000 if exact else 0), grid)
-    return [bytes(out[i * stride:i * stride + int(out_lens[i])]) for i in range(len(units))]
+    crc = np.zeros(len(units), dtype=np.uint32)
+    lib().emu_compress_batch(C.byref(b), (1 if with_header else 0) | (0x400 if hybrid else 0) | (chains << 20), grid,
+                             C.c_void_p(crc.ctypes.data if crcs else None))
+    res = [bytes(out[i * stride:i * stride + int(out_lens[i])]) for i in range(len(units))]
+    if crcs:
+        return res, [int(x) for x in crc]
+    if statuses:
+        return res, [(ERR.get(e.code, str(e.code)), e.a, e.b) for e in st]
+    return res
 
 
 def decompress_units(streams, caps, grid=1, block=32):

@@ -21,15 +21,15 @@ def blocks_of(data):
 def test_k1_k2_corpus_blocks(oracle, name):
     blocks = blocks_of(corpus(name))[:3]
     want = [oracle.compress(b) for b in blocks]
-    assert emu.compress_units(blocks, grid=2, multi=True) == want          # product default: 7 pairs per CTA
-    assert emu.compress_units(blocks[:1], global_window=True) == want[:1]  # one-pair global-window variant
+    assert emu.compress_units(blocks, grid=2) == want                      # 7 shared-memory-table chains per CTA
+    assert emu.compress_units(blocks[:2], hybrid=True) == want[:2]         # ... plus chains with tables in global memory
     for (st, out, guard), b in zip(emu.decompress_units(want, [len(b) for b in blocks], grid=2, block=64), blocks):
         assert st[0] == "Ok" and out == b and guard == b"\xee" * 16
 
 
 def test_k1_small_inputs(oracle):
     units = [b"", b"\x00"] + RANDOM + small_copy_inputs() + small_regular_inputs()[::9]
-    assert emu.compress_units(units, multi=True) == [oracle.compress(u) for u in units]
+    assert emu.compress_units(units) == [oracle.compress(u) for u in units]
     assert emu.compress_units(units, hybrid=True) == [oracle.compress(u) for u in units]
 
 
@@ -78,13 +78,11 @@ def test_k2_fuzz_against_oracle(oracle):
         assert guard == b"\xee" * 16
 
 
-@pytest.mark.parametrize("mode", ["multi", "hybrid", "gw", "sm"])
-def test_k1_adversarial_blocks_all_layouts(oracle, mode):
-    """Every K1 layout (7 pairs per CTA / 7 + 4 pairs with L2-resident tables / global window /
-    shared-memory window) on the rare-path blocks."""
+@pytest.mark.parametrize("hybrid", [False, True])
+def test_k1_adversarial_blocks_both_layouts(oracle, hybrid):
+    """Shared-memory-table chains and chains with the table in global memory on the rare-path blocks."""
     units = adversarial_blocks()
-    got = emu.compress_units(units, multi=(mode == "multi"), hybrid=(mode == "hybrid"), global_window=(mode == "gw"),
-                             parsers=1, grid=2)
+    got = emu.compress_units(units, hybrid=hybrid, grid=2)
     assert [i for i, (c, u) in enumerate(zip(got, units)) if c != oracle.compress(u)] == []
 
 
@@ -95,44 +93,22 @@ def test_k1_fewer_chains_per_cta(oracle, chains):
     assert emu.compress_units(units, hybrid=True, chains=chains, grid=2) == [oracle.compress(u) for u in units]
 
 
-def test_k1_mbarrier_wakeup(oracle):
-    """Experimental emitter wake-up through an mbarrier (-DK1_MBAR build) instead of sleep-polling."""
-    units = adversarial_blocks()[:16] + [corpus("alice29.txt")[:65536], corpus("kppkn.gtb")[:65536], b"", b"ab"]
-    assert emu.compress_units(units, hybrid=True, mbar=True) == [oracle.compress(u) for u in units]
+def test_k1_fused_chunk_checksum(oracle):
+    """Frame encode: the emitter warp computes the chunk's masked CRC-32C beside the compress call."""
+    units = [corpus("alice29.txt")[:65536], corpus("html")[100:40000], b"", b"a", b"abc" * 11, RANDOM[0], corpus("fireworks.jpeg")[3:65539]]
+    got, crc = emu.compress_units(units, hybrid=True, crcs=True)
+    assert got == [oracle.compress(u) for u in units]
+    assert crc[:2] + crc[3:] == [oracle.crc32c_masked(u) for u in units[:2] + units[3:]]
 
 
-def test_k1_speculative_slot_reads(oracle):
-    """Experimental -DK1_GT_SPEC path: L2-table chains read the next window's slots before the commit and revalidate."""
-    units = adversarial_blocks() + [corpus("alice29.txt")[:65536], corpus("html")[:65536], corpus("urls.10K")[:65536]]
-    assert emu.compress_units(units, hybrid=True, gt_spec=True) == [oracle.compress(u) for u in units]
-
-
-@pytest.mark.parametrize("hybrid,aligned,gt", [(False, False, False), (True, False, False), (False, True, False), (True, False, True)])
-def test_k1_wide_step(oracle, hybrid, aligned, gt):
-    """Experimental -DK1_W64 path: 64 positions per parser step on the shared-memory-table chains
-    (gt: also on the L2-table chains, with the match.any commit of -DK1_W64_GT)."""
-    units = adversarial_blocks() + [b"", b"a", RANDOM[0]] + small_copy_inputs()[::7]
-    for name in ("alice29.txt", "html", "urls.10K", "kppkn.gtb", "geo.protodata", "fireworks.jpeg"):
-        units += blocks_of(corpus(name))[:2]
-    got = emu.compress_units(units, multi=not hybrid, hybrid=hybrid, w64=True, w64_aligned=aligned, w64_gt=gt, grid=2)
-    assert [i for i, (g, u) in enumerate(zip(got, units)) if g != oracle.compress(u)] == []
-
-
-def test_k1_unaligned_windows(oracle):
-    """Experimental -DK1_UNALIGNED path: 32-position windows that start where the parse stands."""
-    units = adversarial_blocks() + [b"", b"a"] + small_copy_inputs()[::7]
-    for name in ("alice29.txt", "html", "urls.10K", "kppkn.gtb", "fireworks.jpeg"):
-        units += blocks_of(corpus(name))[:2]
-    got = emu.compress_units(units, hybrid=True, unaligned=True, grid=2)
-    assert [i for i, (g, u) in enumerate(zip(got, units)) if g != oracle.compress(u)] == []
-    got = emu.compress_units(units[:40], hybrid=True, unaligned=True, w64=True, gt_spec=True)   # all experiments together
-    assert [i for i, (g, u) in enumerate(zip(got, units[:40])) if g != oracle.compress(u)] == []
-
-
-def test_k1_pipelined_parsers(oracle):
-    """The NP=2 token-passing variant (kept behind SNAPB200_K1_NP) stays bit-exact."""
-    units = adversarial_blocks()[:12] + [corpus("alice29.txt")[:65536], corpus("html")[:65536]]
-    assert emu.compress_units(units, parsers=2) == [oracle.compress(u) for u in units]
+def test_k1_unit_limits_reported():
+    """A unit above 64KB or a slot below max_compress_len is skipped with out_len 0 and the reference's error."""
+    units = [b"a" * 100, b"b" * 70000, b"hello hello hello hello"]
+    got, st = emu.compress_units(units, statuses=True)
+    assert got[1] == b"" and st[1] == ("TooBig", 70000, 65536)
+    assert st[0][0] == "Ok" and st[2][0] == "Ok" and got[0] and got[2]
+    got, st = emu.compress_units(units[:1], out_cap=100, statuses=True)
+    assert got[0] == b"" and st[0] == ("BufferTooSmall", 100, 32 + 100 + 16)
 
 
 def test_k2_adversarial_blocks(oracle):

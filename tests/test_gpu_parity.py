@@ -522,3 +522,189 @@ def test_property_frame_roundtrip_stream(snap, oracle):
         # single write_all == oracle's single-stream bytes
         w2 = snap.write.FrameEncoder(io.BytesIO()); w2.write_all(data)
         assert w2.into_inner().getvalue() == oracle.frame_encode(data)
+
+
+def test_packed_host_batch(snap, oracle):
+    """sb_compress_batch_host_packed: the library packs densely and reports offsets (no foreknowledge of sizes)."""
+    import gpu_helpers
+    units = adversarial_blocks()[:20] + [b"", b"x", corpus("alice29.txt")[:65536], corpus("html")[:50000]]
+    for name in ("urls.10K", "kppkn.gtb"):
+        d = corpus(name)
+        units += [d[i:i + 65536] for i in range(0, len(d), 65536)]
+    units = units * 40                      # several waves (64 MiB first wave)
+    got, dense, total = gpu_helpers.compress_batch_host_packed(units)
+    want = [oracle.compress(u) for u in units[:len(units) // 40]] * 40
+    assert got == want and dense and total == sum(len(w) for w in want)
+
+
+def test_device_frame_encode_decode_ws(snap, oracle):
+    """Stream-ordered frame encode/decode with caller scratch: bytes == write::FrameEncoder, decode with the
+    encoder's chunk index (parallel parse) and without it (serial walk) give the data back."""
+    import gpu_helpers
+    for name, cut in (("alice29.txt", None), ("fireworks.jpeg", None), ("html", 70000), ("paper-100k.pdf", 65536), ("geo.protodata", 1)):
+        data = corpus(name)[:cut] if cut else corpus(name)
+        stream, offs, res = gpu_helpers.frame_encode_device_ws(data)
+        assert res.status.code == 0 and res.nchunks == (len(data) + 65535) // 65536
+        assert stream == oracle.frame_encode(data)
+        assert offs[0] == 10 and offs[-1] == len(stream)
+        for kw in (dict(index=offs), dict(index=None), dict(index=offs, ws=True), dict(index=None, ws=True)):
+            st, out = gpu_helpers.frame_decode_device(stream, len(data), **kw)
+            assert st[0] == "Ok" and out == data, (name, kw)
+    # a rank's fragment: no stream identifier
+    data = corpus("lcet10.txt")[:200000]
+    stream, offs, res = gpu_helpers.frame_encode_device_ws(data, ident=False)
+    assert stream == oracle.frame_encode(data)[10:] and offs[0] == 0
+    for kw in (dict(index=offs), dict(index=None)):
+        st, out = gpu_helpers.frame_decode_device(stream, len(data), fragment=True, **kw)
+        assert st[0] == "Ok" and out == data
+    st, out = gpu_helpers.frame_decode_device(stream, len(data), index=None)      # without the flag: StreamHeader
+    assert st[0] == "StreamHeader"
+
+
+def test_device_frame_decode_errors(snap, oracle):
+    """The device decoder reports the reference's first error in stream order and the bytes before it."""
+    import gpu_helpers
+    from oracle.oracle import OracleError
+    ident = b"\xff\x06\x00\x00sNaPpY"
+    data = corpus("alice29.txt")[:150000]
+    good = oracle.frame_encode(data)
+    flip = bytearray(good); flip[len(good) // 2] ^= 0x10         # payload damage in the middle chunk
+    crc = bytearray(good); crc[14] ^= 1                           # checksum field of chunk 0
+    streams = [bytes(flip), bytes(crc), good[:-7], good + b"\x00\x07", ident + b"\x02\x00\x00\x00",
+               ident + b"\x80\x03\x00\x00xyz" + b"\xfe\x02\x00\x00\x00\x00" + ident + good[10:],
+               ident + b"\x00\x05\x00\x00\x00\x00\x00\x00\x80", b"123", ident + b"\x01\x03\x00\x00abc"]
+    for s in streams:
+        try:
+            want = (("Ok", 0, 0, 0), oracle.frame_decode(s))
+        except OracleError as e:
+            want = (e.err, None)
+        st, out = gpu_helpers.frame_decode_device(s, 200000)
+        assert st == want[0], (s[:20], st, want[0])
+        if want[1] is not None:
+            assert out == want[1]
+        else:
+            assert data.startswith(out)                           # everything before the failing chunk was produced
+    # a wrong index falls back to the serial walk and still decodes
+    idx = [10, 50, len(good)]
+    st, out = gpu_helpers.frame_decode_device(good, len(data), index=idx)
+    assert st[0] == "Ok" and out == data
+    # output too small
+    st, out = gpu_helpers.frame_decode_device(good, 1000)
+    assert st[:3] == ("BufferTooSmall", 1000, len(data))
+
+
+def test_device_batch_unit_limits(snap):
+    """K1 skips a unit above 64KB or with a slot below max_compress_len and says why."""
+    import ctypes as C
+    import torch
+    import gpu_helpers
+    L = gpu_helpers.lib()
+    dev = torch.device("cuda:0")
+    t_in = torch.zeros(3 * 80000, dtype=torch.uint8, device=dev)
+    lens = torch.tensor([100, 70000, 65536], dtype=torch.int32, device=dev)
+    t_out = torch.zeros(3 * 76544, dtype=torch.uint8, device=dev)
+    out_lens = torch.full((3,), 7, dtype=torch.int32, device=dev)
+    st = torch.zeros(3 * 32, dtype=torch.uint8, device=dev)
+    b = gpu_helpers.batch_from_tensors(t_in, 80000, 0, t_out, 76544, 76544, out_lens, st, 3, in_lens_t=lens)
+    e = snap._lib.SbError()
+    assert L.sb_compress_batch_device(C.byref(b), torch.cuda.current_stream().cuda_stream, C.byref(e)) == 0
+    torch.cuda.synchronize()
+    codes = [int.from_bytes(bytes(st[32 * i:32 * i + 4].cpu().numpy()), "little") for i in range(3)]
+    assert codes == [0, 1, 0] and int(out_lens[1]) == 0 and int(out_lens[0]) > 0 and int(out_lens[2]) > 0
+    # uniform length above the block limit is refused on the host
+    b2 = gpu_helpers.batch_from_tensors(t_in, 80000, 70000, t_out, 76544, 76544, out_lens, None, 3)
+    assert L.sb_compress_batch_device(C.byref(b2), torch.cuda.current_stream().cuda_stream, C.byref(e)) == 1
+
+
+def test_steady_state_allocates_nothing(snap, oracle):
+    """After sb_reserve / a first call the host entry points perform no cudaMalloc, cudaHostAlloc or event creation."""
+    import ctypes as C
+    import gpu_helpers
+    L = gpu_helpers.lib()
+    units = [corpus("alice29.txt")[:65536]] * 300
+    e = snap._lib.SbError()
+    assert L.sb_reserve(4096, 64 << 20, 96 << 20, C.byref(e)) == 0
+    gpu_helpers.compress_batch_host_packed(units)
+    comp = [oracle.compress(units[0])] * 300
+    gpu_helpers.decompress_batch_host(comp, [65536] * 300)
+    before = L.sb_alloc_count()
+    for _ in range(3):
+        got, dense, _t = gpu_helpers.compress_batch_host_packed(units)
+        assert got == comp
+        res = gpu_helpers.decompress_batch_host(comp, [65536] * 300)
+        assert all(r[0][0] == "Ok" for r in res)
+    assert L.sb_alloc_count() == before
+
+
+def test_first_use_from_many_threads(snap, oracle):
+    """Concurrent first calls initialise the device context once (get_ctx was not thread safe).
+    Runs in a child process so that the context is really uninitialised."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child = r"""
+import sys, threading
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import torch; torch.cuda.set_device(0)
+import gpu_helpers
+from oracle import oracle
+snap = gpu_helpers.snap()
+data = [bytes([i]) * 3000 + b"tail %d" % i for i in range(8)]
+out = [None] * 8
+def work(i):
+    torch.cuda.set_device(0)
+    out[i] = snap.raw.Encoder().compress_vec(data[i])
+ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+[t.start() for t in ts]; [t.join() for t in ts]
+assert out == [oracle.compress(d) for d in data]
+print("THREADS OK")
+"""
+    res = subprocess.run([sys.executable, "-c", child, root], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "THREADS OK" in res.stdout, res.stderr[-2000:]
+
+
+def test_foreign_far_offsets(snap, oracle):
+    """Decode-side completeness: copy-4 elements with offsets above 65535 inside a >64KB raw stream."""
+    rng = random.Random(77)
+    head = bytes(rng.randrange(256) for _ in range(70000))
+    want = head + head[:40] + head[100:131] + head[65500:65560]
+    def lit(b):
+        out = b""
+        for i in range(0, len(b), 60):
+            c = b[i:i + 60]
+            out += bytes([(len(c) - 1) << 2]) + c
+        return out
+    def copy4(length, off):
+        return bytes([((length - 1) << 2) | 3]) + off.to_bytes(4, "little")
+    def varint(v):
+        out = b""
+        while v >= 0x80:
+            out += bytes([v & 0x7F | 0x80]); v >>= 7
+        return out + bytes([v])
+    stream = varint(len(want)) + lit(head) + copy4(40, 70000) + copy4(31, 70040 - 100) + copy4(60, 70071 - 65500)
+    assert oracle.decompress(stream) == want
+    assert depress(snap, stream) == want
+    # an offset beyond everything written so far is the reference's Offset error, also for values >= 2^31
+    for off in (70001, 0x80000000, 0xFFFFFFFF):
+        bad = varint(len(head) + 40) + lit(head) + copy4(40, off)
+        from oracle.oracle import OracleError
+        try:
+            oracle.decompress(bad); w = None
+        except OracleError as e:
+            w = e.err
+        try:
+            depress(snap, bad); g = None
+        except Exception as e:  # noqa: BLE001
+            import gpu_helpers
+            g = gpu_helpers.err_tuple(e)
+        assert g == w and w[0] == "Offset"
+
+
+def test_foreign_100mb_multiblock_stream(snap):
+    """A 100 MB raw stream from a foreign encoder (pyarrow's bundled Google snappy: one stream, many blocks)."""
+    pa = pytest.importorskip("pyarrow")
+    base = corpus("alice29.txt") + corpus("html") + corpus("kppkn.gtb") + corpus("urls.10K")
+    data = (base * (100 * 1000 * 1000 // len(base) + 1))[:100 * 1000 * 1000]
+    comp = pa.compress(data, codec="snappy", asbytes=True)
+    assert depress(snap, comp) == data

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """TEST TOOLING: fuzz the K1 kernel body under the CPU warp emulator against the oracle.
-usage: emu_fuzz_k1.py <seed> <nblocks> [multi|hybrid|spec|w64|w64h|w64a|w64g|una|gw|x]   (SBEMU_ORDER=reverse|shuffle perturbs the lane schedule)"""
+usage: emu_fuzz_k1.py <seed> <nblocks> [multi|hybrid]   (SBEMU_ORDER=reverse|shuffle perturbs the lane schedule)"""
 import os
 import random
 import sys
@@ -57,8 +57,7 @@ def main():
     corp = [open(os.path.join(gold, f), "rb").read() for f in sorted(os.listdir(gold))]
     corp = [c for c in corp if len(c) > 70000]
     units = [gen(rng, corp) for _ in range(nblocks)]
-    got = emu.compress_units(units, multi=(mode in ("multi", "w64", "w64a")), hybrid=(mode in ("hybrid", "spec", "w64h", "una", "w64g")), w64_gt=(mode == "w64g"), unaligned=(mode == "una"), gt_spec=(mode == "spec"), w64=(mode in ("w64", "w64h", "w64a", "w64g")), w64_aligned=(mode == "w64a"),
-                             global_window=(mode == "gw"), exact=(mode == "x"), grid=2)
+    got = emu.compress_units(units, hybrid=(mode == "hybrid"), grid=2)
     bad = [i for i, (g, u) in enumerate(zip(got, units)) if g != oracle.compress(u)]
     print("seed", seed, "mode", mode, "blocks", nblocks, "mismatches", bad)
     return 1 if bad else 0
