@@ -11,7 +11,14 @@ metric  : uncompressed GB/s over the compress+decompress round trip
           = 2 * uncompressed_bytes / (t_compress + t_decompress)
 value   : device-resident (inputs already in HBM), CUDA events, max over ranks
 e2e     : the same round trip through the C ABI with HOST (pinned) buffers,
-          H2D/D2H inside the timed region
+          H2D/D2H inside the timed region; compress uses sb_compress_batch_host_packed
+          (the library packs the streams and reports the offsets: no foreknowledge of sizes)
+parity  : warm-up step: full on-device round trip + masked CRC-32C and length of EVERY
+          compressed block (K3 on the device) against the oracle's fingerprints for a
+          stratified sample of every wave (100% when the host is fast enough)
+side workloads (--workload): urls-decompress (configs[2]), frame (configs[3]: device-resident
+          FrameEncoder/FrameDecoder over a long stream in waves), frame-shard (configs[4]:
+          chunk ranges per rank, wave k's NCCL size+payload all-gather overlapping wave k+1's kernels)
 --impl reference : the reference's CPU implementation of the same path (the
           oracle port -- the Rust crate cannot be built here), all host threads,
           bounded sample per step.
@@ -45,6 +52,47 @@ def host_threads():
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+def effective_cores():
+    """CPU time this process may actually use: the affinity mask capped by the cgroup quota (cpu.max / cfs quota).
+    sched_getaffinity alone ignores container quotas (a 128-thread mask with a 16-core quota is 16 cores)."""
+    n = float(host_threads())
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except (OSError, ValueError):
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except (OSError, ValueError):
+            pass
+    return min(n, quota) if quota else n, quota
+
+
+def cpu_baseline_report(orc, text, seconds):
+    """Oracle port on the host cores, bounded sample, with the numbers needed to judge it: threads used, effective
+    cores (cgroup quota), per-thread rate and a 1-thread figure (reference README.md:135-158: ~0.32-0.39 GB/s
+    compress, ~0.9-1.1 GB/s decompress per thread on text)."""
+    threads = host_threads()
+    eff, quota = effective_cores()
+    tc1, td1, _ = cpu_roundtrip(orc, text, 0, 256, 1)
+    one = 2 * 256 * BLOCK / (tc1 + td1) / 1e9
+    tc, td, _ = cpu_roundtrip(orc, text, 0, 32 * threads, threads)
+    count = max(threads, int(32 * threads / (tc + td) * seconds))
+    tc, td, _ = cpu_roundtrip(orc, text, 0, count, threads)
+    val = 2 * count * BLOCK / (tc + td) / 1e9
+    per_thread = val / threads
+    return {"value": val, "unit": "GB/s", "cores": threads, "effective_cores": eff, "cgroup_cpu_quota": quota, "kind": "port",
+            "sample": "%d of the same 64KB text blocks, compress+decompress, oracle C port of rust-snappy on all host threads" % count,
+            "compress_gbs": count * BLOCK / tc / 1e9, "decompress_gbs": count * BLOCK / td / 1e9,
+            "per_thread_gbs": per_thread, "one_thread_gbs": one,
+            "one_thread_compress_gbs": 256 * BLOCK / tc1 / 1e9, "one_thread_decompress_gbs": 256 * BLOCK / td1 / 1e9,
+            "oversubscribed": bool(per_thread < 0.5 * one)}, count
 
 
 def measured_peak():
@@ -127,6 +175,8 @@ def run_reference(args, rank, world):
     orc.lib()
     text = load_text()
     threads = host_threads()
+    tc1, td1, _ = cpu_roundtrip(orc, text, 0, 256, 1)
+    one_thread = 2 * 256 * BLOCK / (tc1 + td1) / 1e9
     # probe speed, then size each step to ~6 s of CPU work so W+K steps end within minutes
     tc, td, _ = cpu_roundtrip(orc, text, 0, 64 * threads, threads)
     rate = 64 * threads / (tc + td)
@@ -148,7 +198,9 @@ def run_reference(args, rank, world):
         "config": {"workload": "raw 64KB text blocks (BASELINE configs[1] generator), CPU sample of %d blocks per step" % count,
                    "block_bytes": BLOCK},
         "compress_gbs": u / ttot_c / 1e9, "decompress_gbs": u / ttot_d / 1e9,
-        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "effective_cores": effective_cores()[0],
+                         "cgroup_cpu_quota": effective_cores()[1], "kind": "port", "per_thread_gbs": val / threads,
+                         "one_thread_gbs": one_thread, "oversubscribed": bool(val / threads < 0.5 * one_thread),
                          "sample": "%d blocks x 64KB per step, oracle C port of rust-snappy (no rustc in image)" % count},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -169,6 +221,8 @@ def run_ours(args, rank, local_rank, world):
     snap = graft.load_package()
     L = snap._lib.lib()
     err = snap._lib.SbError()
+    # this rank's host thread (and the pinned buffers it allocates from here on) stay on the GPU's NUMA node
+    numa_node = L.sb_bind_host_thread_to_device_numa(local_rank) if not args.no_numa_bind else -2
     text = load_text()
     span = len(text) - BLOCK
     blocks = args.blocks
@@ -181,6 +235,7 @@ def run_ours(args, rank, local_rank, world):
     t_c = torch.empty(wave * STRIDE, dtype=torch.uint8, device=dev)
     t_out = torch.empty(wave * BLOCK, dtype=torch.uint8, device=dev)
     t_clen = torch.zeros(blocks, dtype=torch.int32, device=dev)
+    t_ccrc = torch.zeros(blocks, dtype=torch.int32, device=dev)     # masked CRC-32C of every compressed block (parity)
     t_dlen = torch.zeros(wave, dtype=torch.int32, device=dev)
     t_st = torch.zeros(wave * 4, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
@@ -225,6 +280,9 @@ def run_ours(args, rank, local_rank, world):
             e2.record()
             marks.append((e0, e1, e2))
             if verify:
+                # fingerprint of every compressed block of this wave, on the device (K3 over the slots)
+                bf = batch(t_c.data_ptr(), STRIDE, 0, t_clen.data_ptr() + 4 * lo, 0, 0, 0, t_ccrc.data_ptr() + 4 * lo, 0, cnt)
+                ck(L.sb_crc32c_masked_batch_device(C.byref(bf), stream, C.byref(err)))
                 torch.cuda.synchronize()
                 assert torch.equal(t_in[lo * BLOCK:(lo + cnt) * BLOCK], t_out[:cnt * BLOCK]), "round trip mismatch"
                 assert int(t_st.view(wave, 4)[:cnt, 0].abs().sum()) == 0, "decode status != Ok"
@@ -241,10 +299,26 @@ def run_ours(args, rank, local_rank, world):
     for i in range(args.warmup):
         one_step(verify=(i == 0))
     comp_bytes = int(t_clen.to(torch.int64).sum().item())
-    # sampled bit-exact check of compressed bytes against the oracle (outside the timed region)
+    # Parity of the ENCODER on the whole workload, outside the timed region: length + masked CRC-32C of every
+    # sampled block's compressed stream against the oracle. The sample is stratified over every wave (every
+    # `step`-th block); step = 1 (100%) when the host can fingerprint the rank's blocks in ~parity_seconds.
     parity = None
-    if rank == 0 and not args.no_parity:
+    if not args.no_parity:
+        import numpy as np
         from oracle import oracle as orc
+        threads = host_threads()
+        probe = min(blocks, 8 * threads)
+        secs, _l, _c = orc.fingerprint_blocks_mt(text, BLOCK, first_block, 1, probe, MUL, threads)
+        rate = probe / max(secs, 1e-6)
+        budget = args.parity_seconds / max(1, min(world, 8))        # ranks share the host
+        step = max(1, int(-(-blocks // max(1, int(rate * budget)))))
+        step = min(step, 100)                                        # never below 1% of every wave
+        nsamp = (blocks + step - 1) // step
+        secs, want_len, want_crc = orc.fingerprint_blocks_mt(text, BLOCK, first_block, step, nsamp, MUL, threads)
+        got_len = t_clen.cpu().numpy().astype(np.uint32)[::step][:nsamp]
+        got_crc = t_ccrc.cpu().numpy().astype(np.uint32)[::step][:nsamp]
+        equal = int(((got_len == want_len) & (got_crc == want_crc)).sum())
+        # and the bytes themselves for a few blocks of the last wave
         lo = (nwaves - 1) * wave
         cnt = blocks - lo
         idx = sorted(set([0, cnt - 1] + [(k * 7919) % cnt for k in range(args.parity_samples)]))
@@ -254,8 +328,10 @@ def run_ours(args, rank, local_rank, world):
             got = bytes(t_c[i * STRIDE:i * STRIDE + int(clen[i])].cpu().numpy())
             off = ((first_block + lo + i) * MUL) % span
             ok_n += int(got == orc.compress(text[off:off + BLOCK]))
-        parity = {"blocks_compared": len(idx), "blocks_equal": ok_n}
-        assert ok_n == len(idx), "compressed bytes differ from the oracle"
+        parity = {"blocks_compared": int(nsamp), "blocks_equal": equal, "coverage": nsamp / blocks, "every": step,
+                  "what": "compressed length + masked CRC-32C of every sampled block vs the oracle, all waves",
+                  "bytes_compared": len(idx), "bytes_equal": ok_n, "cpu_seconds": secs}
+        assert equal == nsamp and ok_n == len(idx), "compressed blocks differ from the oracle: %r" % (parity,)
 
     sampler = ClockSampler(local_rank)
     barrier()
@@ -292,6 +368,13 @@ def run_ours(args, rank, local_rank, world):
     if not args.no_e2e:
         e2e = run_e2e(args, snap, L, torch, dev, t_in, t_clen, rank, world)
 
+    # ---------------- N > 1: the frame path's exchange step (sizes + payload all-gather over NCCL), small scale
+    shard = None
+    if world > 1 and not args.no_shard:
+        del t_c, t_out
+        torch.cuda.empty_cache()
+        shard = frame_shard_measure(args, snap, L, torch, dev, rank, world, t_text, len(text), gib_per_rank=args.shard_gib_per_rank,
+                                    steps=max(1, min(args.steps, 2)), warmup=1)
     if rank != 0:
         return
     peak, peak_src = measured_peak()
@@ -313,8 +396,7 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": "batched raw block compress+decompress: %d x 64KB synthetic text blocks per GPU (BASELINE configs[1])" % blocks,
                    "blocks_per_gpu": blocks, "block_bytes": BLOCK, "wave_blocks": wave, "ratio": comp_bytes / u_rank,
                    "l2": "inputs larger than L2 (%.1f GiB per GPU per pass)" % (u_rank / 2**30), "parity": parity,
-                   "wall_s_timed_region": wall,
-                   # which build/knobs produced the line (A/B runs of experimental libraries set these)
+                   "wall_s_timed_region": wall, "numa_node": numa_node,
                    "lib": os.path.basename(os.environ.get("SNAPB200_LIB", "libsnapb200.so")),
                    "k1_ng_env": os.environ.get("SNAPB200_K1_NG")},
         "compress_gbs": u_all * args.steps / (ms_cmax / 1e3) / 1e9,
@@ -327,20 +409,18 @@ def run_ours(args, rank, local_rank, world):
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if shard is not None:
+        line["frame_shard"] = shard
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
-        threads = host_threads()
-        tc, td, _ = cpu_roundtrip(orc, text, 0, 32 * threads, threads)
-        count = max(threads, int(32 * threads / (tc + td) * 12.0))
-        tc, td, _ = cpu_roundtrip(orc, text, 0, count, threads)
-        line["cpu_baseline"] = {"value": 2 * count * BLOCK / (tc + td) / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
-                                "sample": "%d of the same 64KB text blocks, compress+decompress, oracle C port on all host threads" % count,
-                                "compress_gbs": count * BLOCK / tc / 1e9, "decompress_gbs": count * BLOCK / td / 1e9}
+        line["cpu_baseline"], _ = cpu_baseline_report(orc, text, 12.0)
     print(json.dumps(line), flush=True)
 
 
 def run_e2e(args, snap, L, torch, dev, t_in, t_clen, rank, world):
-    """Round trip through sb_compress_batch_host / sb_decompress_batch_host with pinned host buffers."""
+    """Round trip through sb_compress_batch_host_packed / sb_decompress_batch_host with pinned host buffers.
+    Nothing learned in the device-resident pass is passed in: the library packs the compressed streams and
+    reports their offsets, and the decompress call consumes exactly that report."""
     import numpy as np
     avail = 0
     try:
@@ -350,43 +430,39 @@ def run_e2e(args, snap, L, torch, dev, t_in, t_clen, rank, world):
     except OSError:
         pass
     n = min(args.e2e_blocks, args.blocks)
-    while n > 1024 and avail and n * BLOCK * 3.2 * max(1, world) > 0.5 * avail:
+    while n > 1024 and avail and n * BLOCK * 3.4 * max(1, world) > 0.5 * avail:
         n //= 2
     err = snap._lib.SbError()
     h_in = torch.empty(n * BLOCK, dtype=torch.uint8).pin_memory()
     h_in.copy_(t_in[:n * BLOCK])
     cap = int(L.sb_max_compress_len(BLOCK))
-    known = t_clen[:n].cpu().numpy().astype(np.uint64)      # sizes from the device-resident pass
-    h_c = torch.empty(int(known.sum()) + cap, dtype=torch.uint8).pin_memory()   # dense compressed stream
+    c_cap = n * cap                                              # worst case: the only bound a caller has
+    h_c = torch.empty(min(c_cap, int(n * BLOCK * 1.2) + cap), dtype=torch.uint8).pin_memory()
     h_out = torch.empty(n * BLOCK, dtype=torch.uint8).pin_memory()
     in_offs = np.arange(n, dtype=np.uint64) * BLOCK
     in_lens = np.full(n, BLOCK, dtype=np.uint32)
-    caps = np.full(n, cap, dtype=np.uint32)
     c_lens = np.zeros(n, dtype=np.uint32)
     d_lens = np.zeros(n, dtype=np.uint32)
     st = np.zeros(n * 4, dtype=np.uint64)
-    c_offs = np.zeros(n, dtype=np.uint64)
+    c_offs = np.zeros(n + 1, dtype=np.uint64)
+    if L.sb_reserve(1 << 15, 1 << 30, 1 << 30, C.byref(err)):       # wave-sized pools up front: no allocation while timed
+        raise snap.error.from_c(err)
 
     def step():
-        # back-to-back destination offsets -> the library gathers each wave on the device and
-        # drains it with one D2H copy
-        rc = L.sb_compress_batch_host(h_in.data_ptr(), in_offs.ctypes.data, in_lens.ctypes.data, h_c.data_ptr(),
-                                      dense_offs.ctypes.data, caps.ctypes.data, c_lens.ctypes.data, n, C.byref(err))
+        rc = L.sb_compress_batch_host_packed(h_in.data_ptr(), in_offs.ctypes.data, in_lens.ctypes.data, h_c.data_ptr(),
+                                             h_c.numel(), c_offs.ctypes.data, c_lens.ctypes.data, n, C.byref(err))
         if rc:
             raise snap.error.from_c(err)
-        np.cumsum(c_lens[:-1], dtype=np.uint64, out=c_offs[1:])
         rc = L.sb_decompress_batch_host(h_c.data_ptr(), c_offs.ctypes.data, c_lens.ctypes.data, h_out.data_ptr(),
                                         in_offs.ctypes.data, in_lens.ctypes.data, d_lens.ctypes.data, st.ctypes.data, n,
                                         C.byref(err))
         if rc:
             raise snap.error.from_c(err)
 
-    # dense destinations: unit k lands right after unit k-1 (sizes known from the device-resident pass)
-    dense_offs = np.zeros(n, dtype=np.uint64)
-    np.cumsum(known[:-1], dtype=np.uint64, out=dense_offs[1:])
     for _ in range(max(1, args.warmup - 1)):
         step()
     assert bool((d_lens == BLOCK).all()) and torch.equal(h_in, h_out), "e2e round trip mismatch"
+    allocs0 = L.sb_alloc_count()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -404,8 +480,252 @@ def run_e2e(args, snap, L, torch, dev, t_in, t_clen, rank, world):
     cbytes = int(c_lens.astype(np.uint64).sum())
     return {"value": 2 * n * BLOCK * world * args.steps / dt / 1e9, "unit": "GB/s",
             "h2d_bytes_per_step": n * BLOCK + cbytes, "d2h_bytes_per_step": cbytes + n * BLOCK,
-            "blocks_per_gpu": n, "api": "sb_compress_batch_host + sb_decompress_batch_host (pinned host buffers)",
-            "ms_per_step": 1e3 * dt / args.steps}
+            "blocks_per_gpu": n, "api": "sb_compress_batch_host_packed + sb_decompress_batch_host (pinned host buffers; "
+            "offsets reported by the library, none passed in)",
+            "ms_per_step": 1e3 * dt / args.steps, "allocations_in_timed_region": int(L.sb_alloc_count() - allocs0)}
+
+
+# ----------------------------------------------------------------------------- frame workloads
+def _wave_input(L, snap, torch, t_text, text_len, t_pool, pool_waves, wave_bytes, first_chunk, w, stream, err, generated):
+    """Input of wave w: slot w % pool_waves of the resident pool, generated on first use (synthetic text chunks)."""
+    slot = w % pool_waves
+    if slot not in generated or generated[slot] != first_chunk:
+        if L.sb_generate_blocks_device(t_text.data_ptr(), text_len, t_pool.data_ptr() + slot * wave_bytes, BLOCK, BLOCK,
+                                       first_chunk, wave_bytes // BLOCK, MUL, stream, C.byref(err)):
+            raise snap.error.from_c(err)
+        generated[slot] = first_chunk
+    return t_pool.data_ptr() + slot * wave_bytes
+
+
+def frame_shard_measure(args, snap, L, torch, dev, rank, world, t_text, text_len, gib_per_rank, steps, warmup,
+                        wave_gib=1.0, verify=True):
+    """BASELINE configs[4]: a stream of 64KB frames split across ranks. Wave w = global chunks
+    [w*world*W, (w+1)*world*W); rank r encodes its r-th slice (sb_frame_encode_device_ws, stream ordered), the
+    per-rank sizes are all-gathered from the device-side result record and the payload is exchanged with grouped
+    NCCL send/recv straight into the wave's reassembly buffer, overlapping the next wave's kernels.
+    Returns GB/s (uncompressed, all ranks) compute-only and with the exchange."""
+    import torch.distributed as dist
+    err = snap._lib.SbError()
+    wave_bytes = int(wave_gib * (1 << 30)) // BLOCK * BLOCK
+    per_rank = int(gib_per_rank * (1 << 30)) // wave_bytes * wave_bytes
+    nwaves = max(1, per_rank // wave_bytes)
+    W = wave_bytes // BLOCK
+    free_b, _tot = torch.cuda.mem_get_info()
+    pool_waves = max(1, min(nwaves, int((free_b * 0.55 - 4 * wave_bytes * world * 0.7) // wave_bytes)))
+    t_pool = torch.empty(pool_waves * wave_bytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    generated = {}
+    first_wave_hash = {}
+
+    def chunk0(w, r):
+        return (w * world + r) * W                                   # first global chunk of (wave, rank)
+
+    def run(exchange, check=False):
+        state = {"ok": True}
+
+        def on_wave(w, buf, offs, sizes, total):
+            if not (check and w == 0):
+                return
+            # decode the reassembled wave on this rank and compare with every rank's regenerated input
+            t_dec = torch.empty(world * wave_bytes + 64, dtype=torch.uint8, device=dev)
+            res = snap._lib.SbFrameResult()
+            if L.sb_frame_decode_device(buf.data_ptr(), total, t_dec.data_ptr(), world * wave_bytes, None, 0, 0, C.byref(res),
+                                        stream, C.byref(err)):
+                raise snap.error.from_c(err)
+            t_ref = torch.empty(wave_bytes, dtype=torch.uint8, device=dev)
+            good = res.status.code == 0 and res.bytes == world * wave_bytes
+            for r in range(world):
+                L.sb_generate_blocks_device(t_text.data_ptr(), text_len, t_ref.data_ptr(), BLOCK, BLOCK, chunk0(0, r), W, MUL,
+                                            stream, C.byref(err))
+                good = good and bool(torch.equal(t_ref, t_dec[r * wave_bytes:(r + 1) * wave_bytes]))
+            state["ok"] = good
+            first_wave_hash["bytes"] = total
+
+        pipe = snap.shard.WavePipeline(wave_bytes, dist if world > 1 else None, dev, exchange=exchange,
+                                       on_wave=on_wave if check else None)
+        ins = [_wave_input(L, snap, torch, t_text, text_len, t_pool, pool_waves, wave_bytes, chunk0(w, rank), w, stream, err, generated)
+               if w < pool_waves else None for w in range(nwaves)]
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for w in range(nwaves):
+            d_in = ins[w] if ins[w] is not None else t_pool.data_ptr() + (w % pool_waves) * wave_bytes   # pool cycles when the share exceeds HBM
+            pipe.encode(w, d_in, wave_bytes)
+        pipe.flush()
+        e1.record()
+        torch.cuda.synchronize()
+        assert state["ok"], "reassembled wave does not decode to the ranks' inputs"
+        return e0.elapsed_time(e1), pipe.stream_bytes, pipe.nccl_bytes
+
+    run(True, check=verify)                                          # warm-up + verification of wave 0
+    for _ in range(max(0, warmup - 1)):
+        run(True)
+    ms_x = ms_c = 0.0
+    sb = nb = 0
+    for _ in range(steps):
+        m, sb, nb = run(True)
+        ms_x += m
+    for _ in range(steps):
+        m, _a, _b = run(False)
+        ms_c += m
+    tt = torch.tensor([ms_x, ms_c], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_x, ms_c = [float(x) for x in tt.tolist()]
+    u_all = nwaves * wave_bytes * world
+    del t_pool
+    torch.cuda.empty_cache()
+    return {"workload": "frame chunks sharded over %d ranks, %d waves x %.2f GiB per rank (BASELINE configs[4] shape), "
+                        "size all-gather + grouped NCCL send/recv payload all-gather inside the timed region" % (world, nwaves, wave_bytes / 2**30),
+            "uncompressed_bytes_all_ranks": u_all, "stream_bytes": sb, "nvlink_bytes_received_per_rank": nb,
+            "with_allgather_gbs": u_all * steps / (ms_x / 1e3) / 1e9, "compute_only_gbs": u_all * steps / (ms_c / 1e3) / 1e9,
+            "ms_per_step_with_allgather": ms_x / steps, "ms_per_step_compute_only": ms_c / steps,
+            "input_pool_waves": pool_waves, "verified": "wave 0 reassembled on every rank decodes (device frame decoder) to all ranks' inputs" if verify else None}
+
+
+def run_frame_shard(args, rank, local_rank, world):
+    """--workload frame-shard: BASELINE configs[4] as its own line (1 TiB total by default, strong scaling)."""
+    import torch
+    import __graft_entry__ as graft
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    snap = graft.load_package()
+    L = snap._lib.lib()
+    text = load_text()
+    t_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).to(dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.sb_launch_count()
+    res = frame_shard_measure(args, snap, L, torch, dev, rank, world, t_text, len(text), gib_per_rank=args.gib / world,
+                              steps=args.steps, warmup=args.warmup, wave_gib=args.wave_gib)
+    clocks = sampler.stop()
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        print(json.dumps({
+            "metric": "uncompressed GB/s, frame encode sharded over ranks with NCCL all-gather reassembly",
+            "value": res["with_allgather_gbs"], "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms_per_step_with_allgather"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "side_measurement": True,
+            "config": {"workload": res["workload"], "total_gib": args.gib, "verified": res["verified"], "input_pool_waves": res["input_pool_waves"]},
+            "compute_only_gbs": res["compute_only_gbs"], "with_allgather_gbs": res["with_allgather_gbs"],
+            "stream_bytes": res["stream_bytes"], "nvlink_bytes_received_per_rank": res["nvlink_bytes_received_per_rank"],
+            "clocks": clocks, "gpu_launches": int(L.sb_launch_count() - launches0), "peak_source": peak_src}), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def run_frame(args, local_rank):
+    """--workload frame: BASELINE configs[3], FrameEncoder/FrameDecoder over a long synthetic stream on one GPU,
+    device resident, in waves (the 256 GiB stream and its ~155 GiB of frames do not fit 180 GB at once): every wave
+    is frame-encoded (K1 with the chunk CRC in the emitter, scan, gather) and decoded again (header parse from the
+    encoder's chunk index, K2, CRC verify). The first pass checks decode(encode(x)) == x for every wave."""
+    import torch
+    import __graft_entry__ as graft
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    snap = graft.load_package()
+    L = snap._lib.lib()
+    err = snap._lib.SbError()
+    text = load_text()
+    t_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).to(dev)
+    wave_bytes = int(args.wave_gib * (1 << 30)) // BLOCK * BLOCK
+    W = wave_bytes // BLOCK
+    nwaves = max(1, int(args.gib * (1 << 30)) // wave_bytes)
+    cap = L.sb_frame_max_len(wave_bytes)
+    esb, dsb = L.sb_frame_encode_scratch_bytes(wave_bytes), L.sb_frame_decode_scratch_bytes(W + 1)
+    t_enc = torch.empty(cap + 16, dtype=torch.uint8, device=dev)
+    t_dec = torch.empty(wave_bytes + 16, dtype=torch.uint8, device=dev)
+    t_idx = torch.zeros(W + 1, dtype=torch.int64, device=dev)
+    t_res = torch.zeros(16, dtype=torch.int64, device=dev)           # two sb_frame_result records
+    t_scr = torch.empty(max(esb, dsb) + 256, dtype=torch.uint8, device=dev)
+    free_b, _t = torch.cuda.mem_get_info()
+    pool_waves = max(1, min(nwaves, int(free_b * 0.8 // wave_bytes)))
+    t_pool = torch.empty(pool_waves * wave_bytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    generated = {}
+    ev = torch.cuda.Event
+
+    def ck(rc):
+        if rc:
+            raise snap.error.from_c(err)
+
+    def one_pass(verify):
+        marks, total_stream = [], 0
+        for w in range(nwaves):
+            d_in = _wave_input(L, snap, torch, t_text, len(text), t_pool, pool_waves, wave_bytes, w * W, w, stream, err, generated) \
+                if (verify or w < pool_waves) else t_pool.data_ptr() + (w % pool_waves) * wave_bytes
+            e0, e1, e2 = ev(enable_timing=True), ev(enable_timing=True), ev(enable_timing=True)
+            e0.record()
+            ck(L.sb_frame_encode_device_ws(d_in, wave_bytes, t_enc.data_ptr(), cap, 1 if w == 0 else 0, t_idx.data_ptr(),
+                                           t_res.data_ptr(), t_scr.data_ptr(), esb + 256, stream, C.byref(err)))
+            e1.record()
+            # the decoder takes the stream length from the index the encoder just wrote (t_idx[W]), all on the device:
+            # cap is the only host-side size
+            n_stream = int(t_idx[W].item()) if verify else one_pass.sizes[w]
+            ck(L.sb_frame_decode_device_ws(t_enc.data_ptr(), n_stream, t_dec.data_ptr(), wave_bytes, t_idx.data_ptr(), W,
+                                           0 if w == 0 else 1, t_res.data_ptr() + 64, t_scr.data_ptr(), dsb + 256, W + 1, stream,
+                                           C.byref(err)))
+            e2.record()
+            marks.append((e0, e1, e2))
+            if verify:
+                torch.cuda.synchronize()
+                one_pass.sizes[w] = n_stream
+                assert int(t_res[0].item()) & 0xFFFFFFFF == 0 and int(t_res[8].item()) & 0xFFFFFFFF == 0, \
+                    "frame status != Ok: wave %d encode %r decode %r" % (w, t_res[:6].tolist(), t_res[8:14].tolist())
+                assert int(t_res[12].item()) == wave_bytes, "decoder produced %d bytes" % int(t_res[12].item())
+                assert torch.equal(t_dec[:wave_bytes], t_pool[(w % pool_waves) * wave_bytes:(w % pool_waves + 1) * wave_bytes]), "frame round trip mismatch"
+            total_stream += one_pass.sizes[w]
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b, _ in marks), sum(b.elapsed_time(c) for _, b, c in marks), total_stream
+
+    one_pass.sizes = [0] * nwaves
+    one_pass(True)
+    # first chunks of the stream against the oracle's FrameEncoder bytes
+    from oracle import oracle as orc
+    span = len(text) - BLOCK
+    head = b"".join(text[(i * MUL) % span:][:BLOCK] for i in range(4))
+    ck(L.sb_frame_encode_device_ws(t_pool.data_ptr(), wave_bytes, t_enc.data_ptr(), cap, 1, t_idx.data_ptr(), t_res.data_ptr(),
+                                   t_scr.data_ptr(), esb + 256, stream, C.byref(err)))
+    torch.cuda.synchronize()
+    want = orc.frame_encode(head)
+    assert bytes(t_enc[:len(want)].cpu().numpy()) == want, "frame bytes differ from the oracle"
+    for _ in range(max(0, args.warmup - 1)):
+        one_pass(False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.sb_launch_count()
+    ms_e = ms_d = 0.0
+    for _ in range(args.steps):
+        a, b, stream_bytes = one_pass(False)
+        ms_e += a
+        ms_d += b
+    clocks = sampler.stop()
+    u = nwaves * wave_bytes
+    peak, peak_src = measured_peak()
+    enc = u * args.steps / (ms_e / 1e3) / 1e9
+    dec = u * args.steps / (ms_d / 1e3) / 1e9
+    print(json.dumps({
+        "metric": "uncompressed GB/s, FrameEncoder + FrameDecoder round trip (device resident)",
+        "value": 2 * u * args.steps / ((ms_e + ms_d) / 1e3) / 1e9, "unit": "GB/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": (ms_e + ms_d) / args.steps, "higher_is_better": True, "dtype": "u8",
+        "data": "synthetic", "side_measurement": True,
+        "config": {"workload": "FrameEncoder/FrameDecoder over a %.0f GiB synthetic text stream in %d waves of %.1f GiB on 1 B200 (BASELINE configs[3])"
+                               % (u / 2**30, nwaves, wave_bytes / 2**30), "stream_bytes": stream_bytes, "ratio": stream_bytes / u,
+                   "input_pool_waves": pool_waves,
+                   "parity": "every wave: decode(encode(x)) == x on device, statuses Ok; first 4 chunks == oracle FrameEncoder bytes"},
+        "frame_encode_gbs": enc, "frame_decode_gbs": dec,
+        "roofline": {"bound": "hbm", "kernel": "k1_m7_kernel (frame encode: K1 + fused CRC, scan, gather)", "achieved": (u + stream_bytes) * args.steps / (ms_e / 1e3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": (u + stream_bytes) * args.steps / (ms_e / 1e3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                     "k5_decode_kernel": {"achieved": (u + stream_bytes) * args.steps / (ms_d / 1e3) / 1e9,
+                                          "frac": (u + stream_bytes) * args.steps / (ms_d / 1e3) / 1e9 / peak}},
+        "clocks": clocks, "gpu_launches": int(L.sb_launch_count() - launches0)}), flush=True)
 
 
 def run_urls(args, local_rank):
@@ -486,9 +806,16 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="text-roundtrip", choices=["text-roundtrip", "urls-decompress"],
-                    help="urls-decompress = BASELINE configs[2] (data/urls.10K tiled), decompress only; a side measurement")
+    ap.add_argument("--parity-seconds", type=float, default=20.0, help="host time budget of the full-coverage fingerprint check")
+    ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--no-shard", action="store_true", help="N>1: skip the frame-shard exchange sub-measurement")
+    ap.add_argument("--shard-gib-per-rank", type=float, default=4.0)
+    ap.add_argument("--workload", default="text-roundtrip", choices=["text-roundtrip", "urls-decompress", "frame", "frame-shard"],
+                    help="side measurements: urls-decompress = BASELINE configs[2]; frame = configs[3] (--gib, default 256); "
+                         "frame-shard = configs[4] (--gib total over all ranks, default 1024)")
     ap.add_argument("--urls-gib", type=float, default=64.0)
+    ap.add_argument("--gib", type=float, default=None)
+    ap.add_argument("--wave-gib", type=float, default=None)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -500,6 +827,16 @@ def main():
         return
     if args.workload == "urls-decompress":
         run_urls(args, local_rank)
+        return
+    if args.workload == "frame":
+        args.gib = args.gib or 256.0
+        args.wave_gib = args.wave_gib or 4.0
+        run_frame(args, local_rank)
+        return
+    if args.workload == "frame-shard":
+        args.gib = args.gib or 1024.0
+        args.wave_gib = args.wave_gib or 1.0
+        run_frame_shard(args, rank, local_rank, world)
         return
     run_ours(args, rank, local_rank, world)
     if world > 1:

@@ -99,7 +99,8 @@ int sb_compress_batch_host_packed(const uint8_t* in_base, const uint64_t* in_off
 
 /* ---- batched device API: device pointers, stream ordered ------------------
  * The kernels' native interface (and what bench.py's `value` times). All
- * pointers are device pointers; `stream` is a cudaStream_t passed as void*.
+ * pointers are device pointers; `stream` is a cudaStream_t passed as void*
+ * (NULL is the legacy default stream, exactly as in the CUDA runtime).
  * Addressing is base + i*stride (uniform) -- or per-unit pointer arrays when
  * in_ptrs/out_ptrs are non-NULL. in_lens/out_caps NULL => the uniform value. */
 typedef struct sb_batch {

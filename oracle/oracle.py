@@ -66,6 +66,9 @@ def lib():
         L.orc_bench_compress_mt.restype = C.c_double
         L.orc_bench_compress_mt.argtypes = [u8p, sz, sz, C.c_uint64, C.c_uint64, C.c_uint64,
                                             C.c_int, C.POINTER(C.c_uint64)]
+        L.orc_fingerprint_blocks_mt.restype = C.c_double
+        L.orc_fingerprint_blocks_mt.argtypes = [u8p, sz, sz, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
+                                                C.c_void_p, C.c_void_p]
         L.orc_bench_decompress_mt.restype = C.c_double
         L.orc_bench_decompress_mt.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), sz,
                                               C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
@@ -158,6 +161,17 @@ def bench_compress_mt(text: bytes, block_len: int, first: int, count: int, mul: 
     tot = C.c_uint64(0)
     secs = lib().orc_bench_compress_mt(text, len(text), block_len, first, count, mul, threads, C.byref(tot))
     return secs, tot.value
+
+
+def fingerprint_blocks_mt(text: bytes, block_len: int, base: int, step: int, count: int, mul: int, threads: int):
+    """(seconds, lens, crcs) of generator blocks base, base+step, ...: compressed length and masked CRC-32C of the
+    compressed stream (bench.py's full-coverage parity check)."""
+    import numpy as np
+    lens = np.zeros(max(count, 1), dtype=np.uint32)
+    crcs = np.zeros(max(count, 1), dtype=np.uint32)
+    secs = lib().orc_fingerprint_blocks_mt(text, len(text), block_len, base, step, count, mul, threads,
+                                           lens.ctypes.data, crcs.ctypes.data)
+    return secs, lens[:count], crcs[:count]
 
 
 def bench_decompress_mt(streams, count: int, threads: int):

@@ -464,6 +464,7 @@ typedef struct {
     const uint8_t *text; size_t text_len, block_len; uint64_t first, count, mul;
     const uint8_t *const *streams; const size_t *lens; size_t nstreams;
     uint64_t total; int mode;
+    uint64_t step, base; uint32_t *out_crcs, *out_lens;   /* mode 2: fingerprints of sampled blocks */
 } job_t;
 
 static void *worker(void *arg) {
@@ -476,6 +477,19 @@ static void *worker(void *arg) {
         for (uint64_t i = 0; i < j->count; i++) {
             uint64_t off = ((j->first + i) * j->mul) % span;
             total += encode_stream(j->text + off, j->block_len, out, table);
+        }
+        free(out); free(table);
+    } else if (j->mode == 2) {
+        /* sample k (k = first .. first+count) is block base + k*step: compressed length + masked CRC of the stream */
+        uint16_t *table = (uint16_t *)malloc(MAX_TABLE_SIZE * sizeof(uint16_t));
+        uint8_t *out = (uint8_t *)malloc(orc_max_compress_len(j->block_len));
+        uint64_t span = (uint64_t)(j->text_len - j->block_len);
+        for (uint64_t k = j->first; k < j->first + j->count; k++) {
+            uint64_t off = ((j->base + k * j->step) * j->mul) % span;
+            size_t n = encode_stream(j->text + off, j->block_len, out, table);
+            j->out_lens[k] = (uint32_t)n;
+            j->out_crcs[k] = orc_crc32c_masked(out, n);
+            total += n;
         }
         free(out); free(table);
     } else {
@@ -518,6 +532,16 @@ double orc_bench_compress_mt(const uint8_t *text, size_t text_len, size_t block_
     job_t p; memset(&p, 0, sizeof p);
     p.text = text; p.text_len = text_len; p.block_len = block_len; p.first = first; p.mul = stride_mul; p.mode = 0;
     return run_mt(p, count, threads, out_total);
+}
+
+/* Parity fingerprints for bench.py: sample k in [0, count) is generator block base + k*step; its compressed
+ * length and the masked CRC-32C of its compressed stream go to out_lens[k] / out_crcs[k]. Returns seconds. */
+double orc_fingerprint_blocks_mt(const uint8_t *text, size_t text_len, size_t block_len, uint64_t base, uint64_t step,
+                                 uint64_t count, uint64_t stride_mul, int threads, uint32_t *out_lens, uint32_t *out_crcs) {
+    job_t p; memset(&p, 0, sizeof p);
+    p.text = text; p.text_len = text_len; p.block_len = block_len; p.first = 0; p.mul = stride_mul; p.mode = 2;
+    p.base = base; p.step = step; p.out_lens = out_lens; p.out_crcs = out_crcs;
+    return run_mt(p, count, threads, NULL);
 }
 
 double orc_bench_decompress_mt(const uint8_t *const *streams, const size_t *lens,

@@ -87,6 +87,8 @@ double orc_bench_compress_mt(const uint8_t *text, size_t text_len, size_t block_
                              int threads, uint64_t *out_total);
 /* Decompress `count` streams: stream i is streams[i % nstreams]; output into a
  * per-thread scratch buffer. Returns seconds; *out_total = decompressed bytes. */
+double orc_fingerprint_blocks_mt(const uint8_t *text, size_t text_len, size_t block_len, uint64_t base, uint64_t step,
+                                 uint64_t count, uint64_t stride_mul, int threads, uint32_t *out_lens, uint32_t *out_crcs);
 double orc_bench_decompress_mt(const uint8_t *const *streams, const size_t *lens,
                                size_t nstreams, uint64_t count, int threads,
                                uint64_t *out_total);

@@ -882,7 +882,7 @@ int sb_frame_encode_device_ws(const uint8_t* d_in, uint64_t n, uint8_t* d_out, u
     int rc = get_ctx(&c, err);
     if (rc) return rc;
     rc = compress_stream_ws(*c, d_in, n, d_out, cap, 1, include_ident, d_chunk_offs, d_result, scratch,
-                            stream ? (cudaStream_t)stream : c->s_compute, err);
+                            (cudaStream_t)stream, err);
     if (rc) return rc;
     ok(err);
     return 0;
@@ -896,7 +896,7 @@ int sb_frame_encode_device(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint
     int rc = get_ctx(&c, err);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    cudaStream_t st = (cudaStream_t)stream;
     CK(c->ws[0].need(encode_ws_bytes(n) + sizeof(sb_frame_result) + 256));
     rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
     sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)c->ws[0].p + align_up(encode_ws_bytes(n), 256));
@@ -957,12 +957,20 @@ int sb_frame_decode_device_ws(const uint8_t* d_in, uint64_t n, uint8_t* d_out, u
     Ctx* c;
     int rc = get_ctx(&c, err);
     if (rc) return rc;
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    cudaStream_t st = (cudaStream_t)stream;
     const sbk::DecodePlan p = make_decode_plan(d_in, n, d_out, cap, d_chunk_offs, nchunks, (int)(flags & 1u), d_result, scratch, max_chunks);
     rc = decode_index_phase(*c, p, st, err);
     if (rc) return rc;
     rc = decode_payload_phase(*c, p, st, err);
     if (rc) return rc;
+    if (getenv("SNAPB200_DEBUG_FRAME")) {
+        sbk::DecodeCtl h;
+        cudaStreamSynchronize(st);
+        cudaMemcpy(&h, p.ctl, sizeof h, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[frame decode] n=%llu index_n=%u fragment=%u cap_chunks=%u -> nchunks=%u need_serial=%u produced=%llu walk_err=%u(%llu,%llu) go=%u first_bad=%u\n",
+                (unsigned long long)n, p.index_n, p.fragment, p.cap_chunks, h.nchunks, h.need_serial, (unsigned long long)h.produced,
+                h.walk_err.code, (unsigned long long)h.walk_err.a, (unsigned long long)h.walk_err.b, h.go, h.first_bad);
+    }
     ok(err);
     return 0;
 }
@@ -976,7 +984,7 @@ int sb_frame_decode_device(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint
     int rc = get_ctx(&c, err);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    cudaStream_t st = (cudaStream_t)stream;
     uint64_t maxc = d_chunk_offs ? (uint64_t)nchunks + 1 : n / 1024 + 4096;
     rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
     for (;;) {
