@@ -32,6 +32,7 @@ k1_m7_kernel(sb_batch b, uint32_t flags, uint64_t* rings, uint16_t* gtables, uin
 }
 const int K1_MAX_NG = 7;
 const size_t K1_M7_SMEM = sbk::k1_multi_smem(7, K1_MAX_NG);
+// 48 registers -> 10 CTAs (40 warps) per SM; forcing 12/14 CTAs through launch bounds spills and measured 5% slower
 __global__ void __launch_bounds__(128) k2_decompress_kernel(sb_batch b) { sbk::k2_decompress_body(b); }
 __global__ void __launch_bounds__(256) k3_crc_kernel(sb_batch b) { sbk::k3_crc_body(b); }
 __global__ void __launch_bounds__(256) k4_fill_lens_kernel(uint32_t* lens, uint64_t n, uint32_t nchunks) { sbk::k4_fill_lens_body(lens, n, nchunks); }

@@ -40,3 +40,18 @@ def decode_all(stream) -> bytes:
     if L.sb_frame_decode(ip, n, op, m.value, C.byref(m), C.byref(e)):
         raise from_c(e)
     return bytes(out[:m.value])
+
+
+def decode_all_partial(stream):
+    """Like decode_all, but a failing stream yields (bytes produced before the failure, the exception) instead of
+    raising: what a reader delivers before its n-th read fails."""
+    n = len(stream)
+    ip, k1 = _ptr(stream) if n else (None, None)
+    m, e = C.c_size_t(0), _lib.SbError()
+    L = _lib.lib()
+    if L.sb_frame_decode(ip, n, None, 0, C.byref(m), C.byref(e)):
+        return b"", from_c(e)
+    out = bytearray(max(m.value, 1))
+    op, k2 = _ptr(out)
+    rc = L.sb_frame_decode(ip, n, op, m.value, C.byref(m), C.byref(e))
+    return bytes(out[:m.value]), (from_c(e) if rc else None)

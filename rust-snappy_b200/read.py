@@ -4,6 +4,11 @@ FrameDecoder keeps the reference's chunk state machine (src/read.rs:104-239):
 one chunk is decoded per refill; the raw decode + checksum run on the GPU.
 FrameEncoder (src/read.rs:272-410) turns each underlying read() of <=64KB into
 one chunk, so its output equals write::FrameEncoder's for slice readers.
+
+`FrameDecoder(rdr, batch_chunks=N)` (default 1 = the reference's behaviour: exactly
+one chunk is pulled from the reader per refill) reads AHEAD up to N data chunks and
+decodes them with one device call (header walk, K2, checksum); bytes and errors come
+out in the same order, but the underlying reader is consumed earlier.
 """
 from . import frame
 from .error import Error, UnexpectedEof
@@ -21,8 +26,11 @@ def _read_exact(r, n):
 
 
 class FrameDecoder:
-    def __init__(self, rdr):
+    def __init__(self, rdr, batch_chunks=1):
         self._r = rdr
+        self._batch = max(1, int(batch_chunks))
+        self._pending = None             # error raised once the bytes decoded before it were served (batch mode)
+        self._eof = False
         self._dec = Decoder()
         self._src = bytearray(frame.MAX_COMPRESS_BLOCK_SIZE)
         self._dst = b""
@@ -45,6 +53,8 @@ class FrameDecoder:
                 parts.append(p)
         if size == 0:
             return b""
+        if self._batch > 1:
+            return self._read_batched(size)
         while True:
             if self._dsts < len(self._dst):
                 out = self._dst[self._dsts:self._dsts + size]
@@ -100,6 +110,57 @@ class FrameDecoder:
 
     def read_to_end(self) -> bytes:
         return self.read(-1)
+
+    # -- batch mode: raw chunks are collected (each read from the underlying reader is exactly the one the reference
+    # would issue, only sooner) and handed to the device decoder as one stream; a stream identifier in front of a later
+    # batch stands in for the one this decoder has already seen (identifier chunks may repeat, src/read.rs:166-178)
+    def _read_batched(self, size) -> bytes:
+        while True:
+            if self._dsts < len(self._dst):
+                out = self._dst[self._dsts:self._dsts + size]
+                self._dsts += len(out)
+                return out
+            if self._pending is not None:
+                e, self._pending = self._pending, None
+                raise e
+            if self._eof:
+                return b""
+            seen = self._read_stream_ident
+            raw = bytearray(frame.STREAM_IDENTIFIER) if seen else bytearray()
+            base = len(raw)
+            chunks = 0
+            while chunks < self._batch and not self._eof:
+                head = _read_upto(self._r, 4)
+                raw += head
+                if len(head) < 4:
+                    self._eof = True                         # clean end (0 bytes) or a truncated header
+                    break
+                self._read_stream_ident = True
+                ln = head[1] | (head[2] << 8) | (head[3] << 16)
+                if ln > frame.MAX_COMPRESS_BLOCK_SIZE or 0x02 <= head[0] <= 0x7F:
+                    self._eof = True                         # the decoder stops here with the reference's error
+                    break
+                body = _read_upto(self._r, ln)
+                raw += body
+                if len(body) < ln:
+                    self._eof = True
+                    break
+                if head[0] in (0x00, 0x01):
+                    chunks += 1
+            self._dst, self._dsts = b"", 0
+            if len(raw) > base:
+                self._dst, self._pending = frame.decode_all_partial(bytes(raw))
+
+
+def _read_upto(r, n):
+    """Like read_exact, but a short stream returns what there was."""
+    out = bytearray()
+    while len(out) < n:
+        piece = r.read(n - len(out))
+        if not piece:
+            break
+        out += piece
+    return bytes(out)
 
 
 class FrameEncoder:

@@ -708,3 +708,48 @@ def test_foreign_100mb_multiblock_stream(snap):
     data = (base * (100 * 1000 * 1000 // len(base) + 1))[:100 * 1000 * 1000]
     comp = pa.compress(data, codec="snappy", asbytes=True)
     assert depress(snap, comp) == data
+
+
+def test_streaming_wrappers_batch_mode(snap, oracle):
+    """write::FrameEncoder(batch_chunks=N) queues full chunks for one device call and writes the same bytes;
+    read::FrameDecoder(batch_chunks=N) reads ahead N chunks per device call and yields the same bytes and errors."""
+    import gpu_helpers
+    from oracle.oracle import OracleError
+    rng = random.Random(99)
+    data = corpus("alice29.txt") + corpus("html") + corpus("fireworks.jpeg")[:70000]
+    for pattern in ([65536] * 40, [1000, 65536, 5, 200000, 65536 * 3, 70000], [7] * 3000 + [65536 * 5 + 3]):
+        ref_w, bat_w = snap.write.FrameEncoder(io.BytesIO()), snap.write.FrameEncoder(io.BytesIO(), batch_chunks=16)
+        at = 0
+        for k in pattern:
+            piece = data[at % len(data):][:k]
+            ref_w.write(piece); bat_w.write(piece); at += k
+            if rng.random() < 0.1:
+                ref_w.flush(); bat_w.flush()
+        a, b = ref_w.into_inner().getvalue(), bat_w.into_inner().getvalue()
+        assert a == b
+    framed = oracle.frame_encode(data)
+    for k in (1, 3, 64):
+        assert snap.read.FrameDecoder(io.BytesIO(framed), batch_chunks=k).read_to_end() == data
+        assert snap.read.FrameDecoder(_Dribble(framed, 5000), batch_chunks=k).read_to_end() == data
+    bad = bytearray(framed); bad[len(framed) // 2] ^= 4
+    for s_ in (bytes(bad), framed[:-9], framed + b"\x00\x07", framed[:10] + b"\x02\x00\x00\x00" + framed[10:]):
+        try:
+            want = (None, oracle.frame_decode(s_))
+        except OracleError as e:
+            want = (e.err, None)
+        for k in (1, 4, 64):
+            r = snap.read.FrameDecoder(io.BytesIO(s_), batch_chunks=k)
+            got, parts = None, []
+            try:
+                while True:
+                    p = r.read(100000)
+                    if not p:
+                        break
+                    parts.append(p)
+            except Exception as e:  # noqa: BLE001
+                got = gpu_helpers.err_tuple(e)
+            assert got == want[0], (k, got, want[0])
+            if want[1] is not None:
+                assert b"".join(parts) == want[1]
+            else:
+                assert data.startswith(b"".join(parts))
