@@ -87,19 +87,27 @@ struct DevBuf {
     template <class T> T* as() { return (T*)p; }
 };
 
-struct Ctx {
-    int dev = -1, sms = 0;
-    std::atomic<bool> ready{false};
+// A lane = everything one host call needs besides the K1 scratch: three streams, the events of the wave pipeline,
+// grow-only device staging and pinned descriptors, and a mutex. Two lanes per device: lane 0 serves the compress-side
+// entry points, lane 1 the decompress-side ones, so that a caller running both directions from two threads gets
+// H2D, kernels and D2H of both in flight at once (PCIe is full duplex; K2 fits beside K1's waves).
+struct Lane {
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-    DevBuf rings, gtables, work;   // K1 scratch: event rings, L2-resident tables, unit counter
-    cudaEvent_t k1_done = nullptr; // K1 launches share that scratch: each waits for the previous one, whatever its stream
-    std::mutex k1_mu;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};   // host-batch pipeline
     DevBuf in[2], slots[2], compact[2], lens[2], status[2], ptrs_in[2], ptrs_out[2], caps[2], ws[2];
     void* pinned[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // pinned staging: [0,1] descriptors in, [2,3] results out, [4] scalar results
     size_t pinned_cap[5] = {0, 0, 0, 0, 0};
     std::mutex mu;
 };
+struct Ctx {
+    int dev = -1, sms = 0;
+    std::atomic<bool> ready{false};
+    DevBuf rings, gtables, work;   // K1 scratch: event rings, L2-resident tables, unit counter
+    cudaEvent_t k1_done = nullptr; // K1 launches share that scratch: each waits for the previous one, whatever its stream
+    std::mutex k1_mu;
+    Lane lane[2];
+};
+const int LANE_ENC = 0, LANE_DEC = 1;
 Ctx g_ctx[16];
 std::mutex g_init_mu;
 
@@ -113,28 +121,32 @@ int init_ctx(Ctx& c, int dev, sb_error* err) {
     CK(c.rings.need((size_t)c.sms * (7 + K1_MAX_NG) * sbk::K1_RING_GW * 8));
     CK(c.gtables.need((size_t)c.sms * K1_MAX_NG * sbk::K1_TABLE_BYTES));
     CK(c.work.need(256));
-    g_allocs += 10;
+    g_allocs += 19;
     CK(cudaEventCreateWithFlags(&c.k1_done, cudaEventDisableTiming));
-    for (int k = 0; k < 2; k++) {
-        CK(cudaEventCreateWithFlags(&c.ev_in[k], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c.ev_k[k], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c.ev_out[k], cudaEventDisableTiming));
+    for (Lane& l : c.lane) {
+        for (int k = 0; k < 2; k++) {
+            CK(cudaEventCreateWithFlags(&l.ev_in[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&l.ev_k[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&l.ev_out[k], cudaEventDisableTiming));
+        }
+        CK(cudaStreamCreateWithFlags(&l.s_compute, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&l.s_h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&l.s_d2h, cudaStreamNonBlocking));
     }
-    CK(cudaStreamCreateWithFlags(&c.s_compute, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking));
     return 0;
 }
 void destroy_partial(Ctx& c) {
     if (c.k1_done) { cudaEventDestroy(c.k1_done); c.k1_done = nullptr; }
-    for (int k = 0; k < 2; k++) {
-        if (c.ev_in[k]) { cudaEventDestroy(c.ev_in[k]); c.ev_in[k] = nullptr; }
-        if (c.ev_k[k]) { cudaEventDestroy(c.ev_k[k]); c.ev_k[k] = nullptr; }
-        if (c.ev_out[k]) { cudaEventDestroy(c.ev_out[k]); c.ev_out[k] = nullptr; }
+    for (Lane& l : c.lane) {
+        for (int k = 0; k < 2; k++) {
+            if (l.ev_in[k]) { cudaEventDestroy(l.ev_in[k]); l.ev_in[k] = nullptr; }
+            if (l.ev_k[k]) { cudaEventDestroy(l.ev_k[k]); l.ev_k[k] = nullptr; }
+            if (l.ev_out[k]) { cudaEventDestroy(l.ev_out[k]); l.ev_out[k] = nullptr; }
+        }
+        if (l.s_compute) { cudaStreamDestroy(l.s_compute); l.s_compute = nullptr; }
+        if (l.s_h2d) { cudaStreamDestroy(l.s_h2d); l.s_h2d = nullptr; }
+        if (l.s_d2h) { cudaStreamDestroy(l.s_d2h); l.s_d2h = nullptr; }
     }
-    if (c.s_compute) { cudaStreamDestroy(c.s_compute); c.s_compute = nullptr; }
-    if (c.s_h2d) { cudaStreamDestroy(c.s_h2d); c.s_h2d = nullptr; }
-    if (c.s_d2h) { cudaStreamDestroy(c.s_d2h); c.s_d2h = nullptr; }
 }
 
 // First use per device is serialised (two threads making their first call together run one initialisation);
@@ -158,7 +170,7 @@ int get_ctx(Ctx** out, sb_error* err) {
 
 // Descriptor arrays (pointers, lengths) are staged through pinned memory: an async copy from
 // pageable memory would not overlap with the running kernel.
-int need_pinned(Ctx& c, int slot, size_t n, sb_error* err) {
+int need_pinned(Lane& c, int slot, size_t n, sb_error* err) {
     if (n <= c.pinned_cap[slot]) return 0;
     if (c.pinned[slot]) { CK(cudaFreeHost(c.pinned[slot])); c.pinned[slot] = nullptr; c.pinned_cap[slot] = 0; }
     n += n / 4 + 4096;
@@ -420,27 +432,30 @@ int sb_bind_host_thread_to_device_numa(int device) {
     return node;
 }
 
-// Size the per-device pools of the host entry points ahead of time: waves of up to `wave_units` units,
-// `wave_in_bytes` input bytes and `wave_out_bytes` output bytes then run without any allocation.
+// Size the per-device pools of the host entry points ahead of time: waves of up to `wave_units` units with
+// `wave_in_bytes` uncompressed and `wave_out_bytes` compressed bytes (both lanes) then run without any allocation.
 int sb_reserve(size_t wave_units, size_t wave_in_bytes, size_t wave_out_bytes, sb_error* err) {
     Ctx* c;
     int rc = get_ctx(&c, err);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
-    for (int b = 0; b < 2; b++) {
-        CK(c->in[b].need(wave_in_bytes + wave_units * 16 + 64));
-        CK(c->slots[b].need(wave_units * (size_t)sbk::kSlotStride));
-        CK(c->compact[b].need(wave_out_bytes + wave_units * 16 + 64));
-        CK(c->lens[b].need(wave_units * 4 + 4));
-        CK(c->caps[b].need(wave_units * 8 + 8));
-        CK(c->status[b].need(wave_units * sizeof(sb_error) + 64));
-        CK(c->ptrs_in[b].need(wave_units * 8 + 8));
-        CK(c->ptrs_out[b].need(wave_units * 8 + 8));
-        CK(c->ws[b].need(align_up((wave_units / sbk::K4_TILE + 3) * 8, 256) + align_up((wave_units + 1) * 8, 256) + 1024));
-        rc = need_pinned(*c, b, wave_units * 24 + 64, err); if (rc) return rc;
-        rc = need_pinned(*c, 2 + b, wave_units * (4 + sizeof(sb_error)) + 64, err); if (rc) return rc;
+    for (int ln = 0; ln < 2; ln++) {
+        Lane& l = c->lane[ln];
+        std::lock_guard<std::mutex> lk(l.mu);
+        for (int b = 0; b < 2; b++) {
+            CK(l.in[b].need((ln == LANE_ENC ? wave_in_bytes : wave_out_bytes) + wave_units * 16 + 64));
+            if (ln == LANE_ENC) CK(l.slots[b].need(wave_units * (size_t)sbk::kSlotStride));
+            CK(l.compact[b].need((ln == LANE_ENC ? wave_out_bytes : wave_in_bytes) + wave_units * 16 + 64));
+            CK(l.lens[b].need(wave_units * 4 + 4));
+            CK(l.caps[b].need(wave_units * 8 + 8));
+            CK(l.status[b].need(wave_units * sizeof(sb_error) + 64));
+            CK(l.ptrs_in[b].need(wave_units * 8 + 8));
+            CK(l.ptrs_out[b].need(wave_units * 8 + 8));
+            CK(l.ws[b].need(align_up((wave_units / sbk::K4_TILE + 3) * 8, 256) + align_up((wave_units + 1) * 8, 256) + 1024));
+            rc = need_pinned(l, b, wave_units * 24 + 64, err); if (rc) return rc;
+            rc = need_pinned(l, 2 + b, wave_units * (4 + sizeof(sb_error)) + 64, err); if (rc) return rc;
+        }
+        rc = need_pinned(l, 4, 4096, err); if (rc) return rc;
     }
-    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
     ok(err);
     return 0;
 }
@@ -456,21 +471,22 @@ int sb_compress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* o
     Ctx* c;
     int rc = get_ctx(&c, err);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
-    CK(c->in[0].need(n + 64));
-    CK(c->compact[0].need(need + 64));
-    CK(c->ws[0].need(encode_ws_bytes(n) + sizeof(sb_frame_result) + 256));
-    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
-    if (n) CK(cudaMemcpyAsync(c->in[0].p, in, n, cudaMemcpyHostToDevice, c->s_compute));
-    sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)c->ws[0].p + align_up(encode_ws_bytes(n), 256));
-    rc = compress_stream_ws(*c, c->in[0].as<uint8_t>(), n, c->compact[0].as<uint8_t>(), need, 0, 0, nullptr, d_res, c->ws[0].p, c->s_compute, err);
+    Lane& l = c->lane[LANE_ENC];
+    std::lock_guard<std::mutex> lk(l.mu);
+    CK(l.in[0].need(n + 64));
+    CK(l.compact[0].need(need + 64));
+    CK(l.ws[0].need(encode_ws_bytes(n) + sizeof(sb_frame_result) + 256));
+    rc = need_pinned(l, 4, 4096, err); if (rc) return rc;
+    if (n) CK(cudaMemcpyAsync(l.in[0].p, in, n, cudaMemcpyHostToDevice, l.s_compute));
+    sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)l.ws[0].p + align_up(encode_ws_bytes(n), 256));
+    rc = compress_stream_ws(*c, l.in[0].as<uint8_t>(), n, l.compact[0].as<uint8_t>(), need, 0, 0, nullptr, d_res, l.ws[0].p, l.s_compute, err);
     if (rc) return rc;
-    sb_frame_result* res = (sb_frame_result*)c->pinned[4];
-    CK(cudaMemcpyAsync(res, d_res, sizeof *res, cudaMemcpyDeviceToHost, c->s_compute));
-    CK(cudaStreamSynchronize(c->s_compute));
+    sb_frame_result* res = (sb_frame_result*)l.pinned[4];
+    CK(cudaMemcpyAsync(res, d_res, sizeof *res, cudaMemcpyDeviceToHost, l.s_compute));
+    CK(cudaStreamSynchronize(l.s_compute));
     if (res->status.code) { if (err) *err = res->status; return (int)res->status.code; }
-    CK(cudaMemcpyAsync(out, c->compact[0].p, res->bytes, cudaMemcpyDeviceToHost, c->s_compute));
-    CK(cudaStreamSynchronize(c->s_compute));
+    CK(cudaMemcpyAsync(out, l.compact[0].p, res->bytes, cudaMemcpyDeviceToHost, l.s_compute));
+    CK(cudaStreamSynchronize(l.s_compute));
     *out_n = (size_t)res->bytes;
     ok(err);
     return 0;
@@ -500,28 +516,29 @@ int sb_decompress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t*
     Ctx* c;
     int rc = get_ctx(&c, err);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
-    CK(c->in[0].need(n + 64));
-    CK(c->compact[0].need(dcap + 64));
-    CK(c->status[0].need(sizeof(sb_error) + 16));
-    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
-    CK(cudaMemcpyAsync(c->in[0].p, in, n, cudaMemcpyHostToDevice, c->s_compute));
+    Lane& l = c->lane[LANE_DEC];
+    std::lock_guard<std::mutex> lk(l.mu);
+    CK(l.in[0].need(n + 64));
+    CK(l.compact[0].need(dcap + 64));
+    CK(l.status[0].need(sizeof(sb_error) + 16));
+    rc = need_pinned(l, 4, 4096, err); if (rc) return rc;
+    CK(cudaMemcpyAsync(l.in[0].p, in, n, cudaMemcpyHostToDevice, l.s_compute));
     sb_batch b;
     memset(&b, 0, sizeof b);
-    b.in_base = c->in[0].as<uint8_t>(); b.in_len_uniform = (uint32_t)n;
-    b.out_base = c->compact[0].as<uint8_t>();
+    b.in_base = l.in[0].as<uint8_t>(); b.in_len_uniform = (uint32_t)n;
+    b.out_base = l.compact[0].as<uint8_t>();
     b.out_cap_uniform = cap > SB_MAX_INPUT ? (uint32_t)SB_MAX_INPUT : (uint32_t)cap;
-    b.statuses = c->status[0].as<sb_error>();
-    b.out_lens = (uint32_t*)((uint8_t*)c->status[0].p + sizeof(sb_error));
+    b.statuses = l.status[0].as<sb_error>();
+    b.out_lens = (uint32_t*)((uint8_t*)l.status[0].p + sizeof(sb_error));
     b.count = 1;
-    rc = launch_k2(*c, b, c->s_compute, err);
+    rc = launch_k2(*c, b, l.s_compute, err);
     if (rc) return rc;
     struct Res { sb_error e; uint32_t len; uint32_t pad; };
-    Res* res = (Res*)c->pinned[4];
-    CK(cudaMemcpyAsync(res, c->status[0].p, sizeof(sb_error) + 8, cudaMemcpyDeviceToHost, c->s_compute));
-    CK(cudaStreamSynchronize(c->s_compute));
+    Res* res = (Res*)l.pinned[4];
+    CK(cudaMemcpyAsync(res, l.status[0].p, sizeof(sb_error) + 8, cudaMemcpyDeviceToHost, l.s_compute));
+    CK(cudaStreamSynchronize(l.s_compute));
     if (res->e.code) { if (err) *err = res->e; return (int)res->e.code; }
-    if (res->len) CK(cudaMemcpy(out, c->compact[0].p, res->len, cudaMemcpyDeviceToHost));
+    if (res->len) CK(cudaMemcpy(out, l.compact[0].p, res->len, cudaMemcpyDeviceToHost));
     *out_n = res->len;
     ok(err);
     return 0;
@@ -532,18 +549,19 @@ int sb_crc32c_masked(const uint8_t* in, size_t n, uint32_t* out, sb_error* err) 
     Ctx* c;
     int rc = get_ctx(&c, err);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
-    CK(c->in[0].need(n + 64));
-    CK(c->lens[0].need(16));
-    if (n) CK(cudaMemcpyAsync(c->in[0].p, in, n, cudaMemcpyHostToDevice, c->s_compute));
+    Lane& l = c->lane[LANE_ENC];
+    std::lock_guard<std::mutex> lk(l.mu);
+    CK(l.in[0].need(n + 64));
+    CK(l.lens[0].need(16));
+    if (n) CK(cudaMemcpyAsync(l.in[0].p, in, n, cudaMemcpyHostToDevice, l.s_compute));
     sb_batch b;
     memset(&b, 0, sizeof b);
-    b.in_base = c->in[0].as<uint8_t>(); b.in_len_uniform = (uint32_t)n;
-    b.out_lens = c->lens[0].as<uint32_t>(); b.count = 1;
-    rc = launch_k3(*c, b, c->s_compute, err);
+    b.in_base = l.in[0].as<uint8_t>(); b.in_len_uniform = (uint32_t)n;
+    b.out_lens = l.lens[0].as<uint32_t>(); b.count = 1;
+    rc = launch_k3(*c, b, l.s_compute, err);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(out, c->lens[0].p, 4, cudaMemcpyDeviceToHost, c->s_compute));
-    CK(cudaStreamSynchronize(c->s_compute));
+    CK(cudaMemcpyAsync(out, l.lens[0].p, 4, cudaMemcpyDeviceToHost, l.s_compute));
+    CK(cudaStreamSynchronize(l.s_compute));
     ok(err);
     return 0;
 }
@@ -639,17 +657,18 @@ int compress_batch_host_impl(const uint8_t* in_base, const uint64_t* in_offs, co
     Ctx* c;
     int rc = get_ctx(&c, err);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    Lane& l = c->lane[LANE_ENC];
+    std::lock_guard<std::mutex> lk(l.mu);
     std::vector<Wave> waves = plan_waves(in_lens, count, nullptr);
     std::vector<uint64_t> doff;
     auto stage_in = [&](size_t wi) -> int {
         const Wave& w = waves[wi];
         const int b = (int)(wi & 1);
-        CK(c->in[b].need(w.in_bytes + 64));
-        CK(c->slots[b].need(w.count * (size_t)sbk::kSlotStride));
-        CK(c->lens[b].need(w.count * 4 + 4));
-        CK(c->caps[b].need(w.count * 4 + 4));
-        CK(c->ptrs_in[b].need(w.count * 8 + 8));
+        CK(l.in[b].need(w.in_bytes + 64));
+        CK(l.slots[b].need(w.count * (size_t)sbk::kSlotStride));
+        CK(l.lens[b].need(w.count * 4 + 4));
+        CK(l.caps[b].need(w.count * 4 + 4));
+        CK(l.ptrs_in[b].need(w.count * 8 + 8));
         // coalesce units that are contiguous on the host into single copies
         doff.resize(w.count);
         uint64_t at = 0;
@@ -659,19 +678,19 @@ int compress_batch_host_impl(const uint8_t* in_base, const uint64_t* in_offs, co
             uint64_t run = 0;
             const uint64_t h0 = in_offs[w.first + i];
             while (j < w.count && in_offs[w.first + j] == h0 + run) { doff[j] = at + run; run += in_lens[w.first + j]; j++; }
-            if (run) CK(cudaMemcpyAsync(c->in[b].as<uint8_t>() + at, in_base + h0, run, cudaMemcpyHostToDevice, c->s_h2d));
+            if (run) CK(cudaMemcpyAsync(l.in[b].as<uint8_t>() + at, in_base + h0, run, cudaMemcpyHostToDevice, l.s_h2d));
             at += (run + 15) & ~(uint64_t)15;
             i = j;
         }
         // pinned[b] was last read by the H2D of wave wi-2, whose kernel has completed (the loop below waited for it)
-        { int prc = need_pinned(*c, b, w.count * 12 + 64, err); if (prc) return prc; }
-        uint64_t* ptrs = (uint64_t*)c->pinned[b];
+        { int prc = need_pinned(l, b, w.count * 12 + 64, err); if (prc) return prc; }
+        uint64_t* ptrs = (uint64_t*)l.pinned[b];
         uint32_t* plen = (uint32_t*)(ptrs + w.count);
-        for (size_t k = 0; k < w.count; k++) ptrs[k] = (uint64_t)(uintptr_t)(c->in[b].as<uint8_t>() + doff[k]);
+        for (size_t k = 0; k < w.count; k++) ptrs[k] = (uint64_t)(uintptr_t)(l.in[b].as<uint8_t>() + doff[k]);
         memcpy(plen, in_lens + w.first, w.count * 4);
-        CK(cudaMemcpyAsync(c->ptrs_in[b].p, ptrs, w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
-        CK(cudaMemcpyAsync(c->caps[b].p, plen, w.count * 4, cudaMemcpyHostToDevice, c->s_h2d));
-        CK(cudaEventRecord(c->ev_in[b], c->s_h2d));
+        CK(cudaMemcpyAsync(l.ptrs_in[b].p, ptrs, w.count * 8, cudaMemcpyHostToDevice, l.s_h2d));
+        CK(cudaMemcpyAsync(l.caps[b].p, plen, w.count * 4, cudaMemcpyHostToDevice, l.s_h2d));
+        CK(cudaEventRecord(l.ev_in[b], l.s_h2d));
         return 0;
     };
     const bool timing = getenv("SNAPB200_TIMING") != nullptr;
@@ -683,47 +702,47 @@ int compress_batch_host_impl(const uint8_t* in_base, const uint64_t* in_offs, co
         const Wave& w = waves[wi];
         const int b = (int)(wi & 1);
         if (timing) fprintf(stderr, "[compress wave %zu] t=%.2f launch (count %zu)\n", wi, now_ms() - t_begin, w.count);
-        CK(cudaStreamWaitEvent(c->s_compute, c->ev_in[b], 0));
-        if (wi >= 2) CK(cudaStreamWaitEvent(c->s_compute, c->ev_out[b], 0));   // wave wi-2 (same buffers) fully drained
+        CK(cudaStreamWaitEvent(l.s_compute, l.ev_in[b], 0));
+        if (wi >= 2) CK(cudaStreamWaitEvent(l.s_compute, l.ev_out[b], 0));   // wave wi-2 (same buffers) fully drained
         sb_batch bt;
         memset(&bt, 0, sizeof bt);
-        bt.in_ptrs = (const uint8_t* const*)c->ptrs_in[b].p; bt.in_lens = c->caps[b].as<uint32_t>();
-        bt.out_base = c->slots[b].as<uint8_t>(); bt.out_stride = sbk::kSlotStride; bt.out_cap_uniform = sbk::kSlotStride;
-        bt.out_lens = c->lens[b].as<uint32_t>(); bt.count = (uint32_t)w.count;
-        rc = launch_k1(*c, bt, 1u, nullptr, c->s_compute, err);
+        bt.in_ptrs = (const uint8_t* const*)l.ptrs_in[b].p; bt.in_lens = l.caps[b].as<uint32_t>();
+        bt.out_base = l.slots[b].as<uint8_t>(); bt.out_stride = sbk::kSlotStride; bt.out_cap_uniform = sbk::kSlotStride;
+        bt.out_lens = l.lens[b].as<uint32_t>(); bt.count = (uint32_t)w.count;
+        rc = launch_k1(*c, bt, 1u, nullptr, l.s_compute, err);
         if (rc) return rc;
         // pack the wave's streams back to back on the device (offsets by scan), so the drain is one D2H
         uint64_t worst = 0;
         for (size_t k = 0; k < w.count; k++) worst += sb_max_compress_len(in_lens[w.first + k]);
-        CK(c->compact[b].need(worst + 64));
+        CK(l.compact[b].need(worst + 64));
         const size_t tiles_bytes = align_up((w.count / sbk::K4_TILE + 3) * 8, 256);
-        CK(c->ws[b].need(tiles_bytes + align_up((w.count + 1) * 8, 256) + 1024));
+        CK(l.ws[b].need(tiles_bytes + align_up((w.count + 1) * 8, 256) + 1024));
         sbk::FramePlan p;
         memset(&p, 0, sizeof p);
-        p.slots = c->slots[b].as<uint8_t>(); p.clens = c->lens[b].as<uint32_t>(); p.nchunks = (uint32_t)w.count;
-        p.frame = 0; p.head_len = 0; p.tiles = (uint64_t*)c->ws[b].p; p.offs = (uint64_t*)((uint8_t*)c->ws[b].p + tiles_bytes);
-        p.out = c->compact[b].as<uint8_t>(); p.cap = c->compact[b].cap; p.result = nullptr;
-        rc = launch_assemble(*c, p, c->s_compute, err);
+        p.slots = l.slots[b].as<uint8_t>(); p.clens = l.lens[b].as<uint32_t>(); p.nchunks = (uint32_t)w.count;
+        p.frame = 0; p.head_len = 0; p.tiles = (uint64_t*)l.ws[b].p; p.offs = (uint64_t*)((uint8_t*)l.ws[b].p + tiles_bytes);
+        p.out = l.compact[b].as<uint8_t>(); p.cap = l.compact[b].cap; p.result = nullptr;
+        rc = launch_assemble(*c, p, l.s_compute, err);
         if (rc) return rc;
         // results come back through pinned staging: a D2H copy into the caller's (pageable) array
         // would block this thread until the kernel is done and serialise the next wave's H2D behind it
-        { int prc = need_pinned(*c, 2 + b, w.count * 12 + 64, err); if (prc) return prc; }
-        uint32_t* plens = (uint32_t*)c->pinned[2 + b];
+        { int prc = need_pinned(l, 2 + b, w.count * 12 + 64, err); if (prc) return prc; }
+        uint32_t* plens = (uint32_t*)l.pinned[2 + b];
         uint64_t* poffs = (uint64_t*)(plens + ((w.count + 2) & ~(size_t)1));
-        CK(cudaMemcpyAsync(plens, c->lens[b].p, w.count * 4, cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaMemcpyAsync(poffs, p.offs, (w.count + 1) * 8, cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaEventRecord(c->ev_k[b], c->s_compute));
+        CK(cudaMemcpyAsync(plens, l.lens[b].p, w.count * 4, cudaMemcpyDeviceToHost, l.s_compute));
+        CK(cudaMemcpyAsync(poffs, p.offs, (w.count + 1) * 8, cudaMemcpyDeviceToHost, l.s_compute));
+        CK(cudaEventRecord(l.ev_k[b], l.s_compute));
         if (wi + 1 < waves.size()) { rc = stage_in(wi + 1); if (rc) return rc; }   // overlaps the kernel above
         if (timing) fprintf(stderr, "[compress wave %zu] t=%.2f staged next\n", wi, now_ms() - t_begin);
-        CK(cudaEventSynchronize(c->ev_k[b]));
+        CK(cudaEventSynchronize(l.ev_k[b]));
         memcpy(out_lens + w.first, plens, w.count * 4);
         const uint64_t run = poffs[w.count];
         if (timing) fprintf(stderr, "[compress wave %zu] t=%.2f kernel done (%llu bytes)\n", wi, now_ms() - t_begin, (unsigned long long)run);
-        CK(cudaStreamWaitEvent(c->s_d2h, c->ev_k[b], 0));
+        CK(cudaStreamWaitEvent(l.s_d2h, l.ev_k[b], 0));
         if (packed) {
             if (packed_at + run > out_cap_total) return fail(err, SB_BUFFER_TOO_SMALL, out_cap_total, packed_at + run);
             for (size_t k = 0; k < w.count; k++) out_offs_ret[w.first + k] = packed_at + poffs[k];
-            if (run) CK(cudaMemcpyAsync(out_base + packed_at, c->compact[b].p, run, cudaMemcpyDeviceToHost, c->s_d2h));
+            if (run) CK(cudaMemcpyAsync(out_base + packed_at, l.compact[b].p, run, cudaMemcpyDeviceToHost, l.s_d2h));
             packed_at += run;
         } else {
             // caller's offsets: host-contiguous destinations travel as one copy per run
@@ -733,15 +752,15 @@ int compress_batch_host_impl(const uint8_t* in_base, const uint64_t* in_offs, co
                 uint64_t len = 0;
                 const uint64_t h0 = out_offs_in[w.first + k];
                 while (j < w.count && out_offs_in[w.first + j] == h0 + len) { len += plens[j]; j++; }
-                if (len) CK(cudaMemcpyAsync(out_base + h0, c->compact[b].as<uint8_t>() + poffs[k], len, cudaMemcpyDeviceToHost, c->s_d2h));
+                if (len) CK(cudaMemcpyAsync(out_base + h0, l.compact[b].as<uint8_t>() + poffs[k], len, cudaMemcpyDeviceToHost, l.s_d2h));
                 k = j;
             }
         }
-        CK(cudaEventRecord(c->ev_out[b], c->s_d2h));
+        CK(cudaEventRecord(l.ev_out[b], l.s_d2h));
     }
     if (packed) out_offs_ret[count] = packed_at;
-    CK(cudaStreamSynchronize(c->s_d2h));
-    CK(cudaStreamSynchronize(c->s_compute));
+    CK(cudaStreamSynchronize(l.s_d2h));
+    CK(cudaStreamSynchronize(l.s_compute));
     ok(err);
     return 0;
 }
@@ -776,7 +795,8 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
     Ctx* c;
     int rc = get_ctx(&c, err);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    Lane& l = c->lane[LANE_DEC];
+    std::lock_guard<std::mutex> lk(l.mu);
     std::vector<Wave> waves = plan_waves(in_lens, count, out_caps);
     std::vector<uint64_t> pout[2];
     // H2D of wave wi into buffer set wi&1 (copy stream; overlaps the previous wave's kernel)
@@ -785,15 +805,15 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
         const int b = (int)(wi & 1);
         uint64_t out_total = 0;
         for (size_t k = 0; k < w.count; k++) out_total += ((uint64_t)out_caps[w.first + k] + 15) & ~(uint64_t)15;
-        CK(c->in[b].need(w.in_bytes + 64));
-        CK(c->compact[b].need(out_total + 64));
-        CK(c->lens[b].need(w.count * 4 + 4));
-        CK(c->caps[b].need(w.count * 8 + 8));
-        CK(c->status[b].need(w.count * sizeof(sb_error)));
-        CK(c->ptrs_in[b].need(w.count * 8 + 8));
-        CK(c->ptrs_out[b].need(w.count * 8 + 8));
-        { int prc = need_pinned(*c, b, w.count * 24 + 64, err); if (prc) return prc; }
-        uint64_t* sp = (uint64_t*)c->pinned[b];      // [count] in pointers, [count] out pointers, then lengths and caps
+        CK(l.in[b].need(w.in_bytes + 64));
+        CK(l.compact[b].need(out_total + 64));
+        CK(l.lens[b].need(w.count * 4 + 4));
+        CK(l.caps[b].need(w.count * 8 + 8));
+        CK(l.status[b].need(w.count * sizeof(sb_error)));
+        CK(l.ptrs_in[b].need(w.count * 8 + 8));
+        CK(l.ptrs_out[b].need(w.count * 8 + 8));
+        { int prc = need_pinned(l, b, w.count * 24 + 64, err); if (prc) return prc; }
+        uint64_t* sp = (uint64_t*)l.pinned[b];      // [count] in pointers, [count] out pointers, then lengths and caps
         pout[b].resize(w.count);
         uint64_t at = 0, oat = 0;
         size_t i = 0;
@@ -802,53 +822,53 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
             uint64_t run = 0;
             const uint64_t h0 = in_offs[w.first + i];
             while (j < w.count && in_offs[w.first + j] == h0 + run) {
-                sp[j] = (uint64_t)(uintptr_t)(c->in[b].as<uint8_t>() + at + run); run += in_lens[w.first + j]; j++;
+                sp[j] = (uint64_t)(uintptr_t)(l.in[b].as<uint8_t>() + at + run); run += in_lens[w.first + j]; j++;
             }
-            if (run) CK(cudaMemcpyAsync(c->in[b].as<uint8_t>() + at, in_base + h0, run, cudaMemcpyHostToDevice, c->s_h2d));
+            if (run) CK(cudaMemcpyAsync(l.in[b].as<uint8_t>() + at, in_base + h0, run, cudaMemcpyHostToDevice, l.s_h2d));
             at += (run + 15) & ~(uint64_t)15;
             i = j;
         }
         for (size_t k = 0; k < w.count; k++) {
-            pout[b][k] = (uint64_t)(uintptr_t)(c->compact[b].as<uint8_t>() + oat);
+            pout[b][k] = (uint64_t)(uintptr_t)(l.compact[b].as<uint8_t>() + oat);
             sp[w.count + k] = pout[b][k];
             oat += ((uint64_t)out_caps[w.first + k] + 15) & ~(uint64_t)15;
         }
         uint32_t* sl = (uint32_t*)(sp + 2 * w.count);
         memcpy(sl, in_lens + w.first, w.count * 4);
         memcpy(sl + w.count, out_caps + w.first, w.count * 4);
-        CK(cudaMemcpyAsync(c->ptrs_in[b].p, sp, w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
-        CK(cudaMemcpyAsync(c->ptrs_out[b].p, sp + w.count, w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
-        CK(cudaMemcpyAsync(c->caps[b].p, sl, w.count * 8, cudaMemcpyHostToDevice, c->s_h2d));
-        CK(cudaEventRecord(c->ev_in[b], c->s_h2d));
+        CK(cudaMemcpyAsync(l.ptrs_in[b].p, sp, w.count * 8, cudaMemcpyHostToDevice, l.s_h2d));
+        CK(cudaMemcpyAsync(l.ptrs_out[b].p, sp + w.count, w.count * 8, cudaMemcpyHostToDevice, l.s_h2d));
+        CK(cudaMemcpyAsync(l.caps[b].p, sl, w.count * 8, cudaMemcpyHostToDevice, l.s_h2d));
+        CK(cudaEventRecord(l.ev_in[b], l.s_h2d));
         return 0;
     };
     if (!waves.empty()) { rc = stage_in(0); if (rc) return rc; }
     for (size_t wi = 0; wi < waves.size(); wi++) {
         const Wave& w = waves[wi];
         const int b = (int)(wi & 1);
-        CK(cudaStreamWaitEvent(c->s_compute, c->ev_in[b], 0));
-        if (wi >= 2) CK(cudaStreamWaitEvent(c->s_compute, c->ev_out[b], 0));   // wave wi-2 (same buffers) fully drained
+        CK(cudaStreamWaitEvent(l.s_compute, l.ev_in[b], 0));
+        if (wi >= 2) CK(cudaStreamWaitEvent(l.s_compute, l.ev_out[b], 0));   // wave wi-2 (same buffers) fully drained
         sb_batch bt;
         memset(&bt, 0, sizeof bt);
-        bt.in_ptrs = (const uint8_t* const*)c->ptrs_in[b].p; bt.in_lens = c->caps[b].as<uint32_t>();
-        bt.out_ptrs = (uint8_t* const*)c->ptrs_out[b].p; bt.out_caps = c->caps[b].as<uint32_t>() + w.count;
-        bt.out_lens = c->lens[b].as<uint32_t>(); bt.statuses = c->status[b].as<sb_error>(); bt.count = (uint32_t)w.count;
-        rc = launch_k2(*c, bt, c->s_compute, err);
+        bt.in_ptrs = (const uint8_t* const*)l.ptrs_in[b].p; bt.in_lens = l.caps[b].as<uint32_t>();
+        bt.out_ptrs = (uint8_t* const*)l.ptrs_out[b].p; bt.out_caps = l.caps[b].as<uint32_t>() + w.count;
+        bt.out_lens = l.lens[b].as<uint32_t>(); bt.statuses = l.status[b].as<sb_error>(); bt.count = (uint32_t)w.count;
+        rc = launch_k2(*c, bt, l.s_compute, err);
         if (rc) return rc;
-        { int prc = need_pinned(*c, 2 + b, w.count * (4 + sizeof(sb_error)) + 64, err); if (prc) return prc; }
-        sb_error* pst = (sb_error*)c->pinned[2 + b];
+        { int prc = need_pinned(l, 2 + b, w.count * (4 + sizeof(sb_error)) + 64, err); if (prc) return prc; }
+        sb_error* pst = (sb_error*)l.pinned[2 + b];
         uint32_t* pln = (uint32_t*)(pst + w.count);
-        CK(cudaMemcpyAsync(pln, c->lens[b].p, w.count * 4, cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaMemcpyAsync(pst, c->status[b].p, w.count * sizeof(sb_error), cudaMemcpyDeviceToHost, c->s_compute));
-        CK(cudaEventRecord(c->ev_k[b], c->s_compute));
+        CK(cudaMemcpyAsync(pln, l.lens[b].p, w.count * 4, cudaMemcpyDeviceToHost, l.s_compute));
+        CK(cudaMemcpyAsync(pst, l.status[b].p, w.count * sizeof(sb_error), cudaMemcpyDeviceToHost, l.s_compute));
+        CK(cudaEventRecord(l.ev_k[b], l.s_compute));
         // the next wave's staging writes pout[b^1] only: this wave's pout[b] stays valid for the drain below
         if (wi + 1 < waves.size()) { rc = stage_in(wi + 1); if (rc) return rc; }   // overlaps the kernel above and the previous drain
-        CK(cudaEventSynchronize(c->ev_k[b]));
+        CK(cudaEventSynchronize(l.ev_k[b]));
         memcpy(out_lens + w.first, pln, w.count * 4);
         memcpy(statuses + w.first, pst, w.count * sizeof(sb_error));
         // drain on the third stream; contiguous destinations whose caps are exactly filled go out as one copy
-        CK(cudaStreamWaitEvent(c->s_d2h, c->ev_k[b], 0));
-        const uint64_t cbase = (uint64_t)(uintptr_t)c->compact[b].p;
+        CK(cudaStreamWaitEvent(l.s_d2h, l.ev_k[b], 0));
+        const uint64_t cbase = (uint64_t)(uintptr_t)l.compact[b].p;
         size_t k = 0;
         while (k < w.count) {
             size_t j = k;
@@ -861,13 +881,13 @@ int sb_decompress_batch_host(const uint8_t* in_base, const uint64_t* in_offs, co
                 j++;
                 if (!full) break;
             }
-            if (run) CK(cudaMemcpyAsync(out_base + h0, c->compact[b].as<uint8_t>() + d0, run, cudaMemcpyDeviceToHost, c->s_d2h));
+            if (run) CK(cudaMemcpyAsync(out_base + h0, l.compact[b].as<uint8_t>() + d0, run, cudaMemcpyDeviceToHost, l.s_d2h));
             k = j;
         }
-        CK(cudaEventRecord(c->ev_out[b], c->s_d2h));
+        CK(cudaEventRecord(l.ev_out[b], l.s_d2h));
     }
-    CK(cudaStreamSynchronize(c->s_d2h));
-    CK(cudaStreamSynchronize(c->s_compute));
+    CK(cudaStreamSynchronize(l.s_d2h));
+    CK(cudaStreamSynchronize(l.s_compute));
     ok(err);
     return 0;
 }
@@ -896,14 +916,15 @@ int sb_frame_encode_device(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint
     Ctx* c;
     int rc = get_ctx(&c, err);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    Lane& l = c->lane[LANE_ENC];
+    std::lock_guard<std::mutex> lk(l.mu);
     cudaStream_t st = (cudaStream_t)stream;
-    CK(c->ws[0].need(encode_ws_bytes(n) + sizeof(sb_frame_result) + 256));
-    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
-    sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)c->ws[0].p + align_up(encode_ws_bytes(n), 256));
-    rc = compress_stream_ws(*c, d_in, n, d_out, cap, 1, include_ident, nullptr, d_res, c->ws[0].p, st, err);
+    CK(l.ws[0].need(encode_ws_bytes(n) + sizeof(sb_frame_result) + 256));
+    rc = need_pinned(l, 4, 4096, err); if (rc) return rc;
+    sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)l.ws[0].p + align_up(encode_ws_bytes(n), 256));
+    rc = compress_stream_ws(*c, d_in, n, d_out, cap, 1, include_ident, nullptr, d_res, l.ws[0].p, st, err);
     if (rc) return rc;
-    sb_frame_result* res = (sb_frame_result*)c->pinned[4];
+    sb_frame_result* res = (sb_frame_result*)l.pinned[4];
     CK(cudaMemcpyAsync(res, d_res, sizeof *res, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (res->status.code) { if (err) *err = res->status; return (int)res->status.code; }
@@ -923,22 +944,23 @@ int sb_frame_encode_ex(const uint8_t* in, size_t n, uint8_t* out, size_t cap, si
     Ctx* c;
     int rc = get_ctx(&c, err);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
-    CK(c->in[1].need(n + 64));
-    CK(c->compact[1].need(sb_frame_max_len(n) + 64));
-    CK(c->ws[1].need(encode_ws_bytes(n) + sizeof(sb_frame_result) + 256));
-    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
-    CK(cudaMemcpyAsync(c->in[1].p, in, n, cudaMemcpyHostToDevice, c->s_compute));
-    sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)c->ws[1].p + align_up(encode_ws_bytes(n), 256));
-    rc = compress_stream_ws(*c, c->in[1].as<uint8_t>(), n, c->compact[1].as<uint8_t>(), sb_frame_max_len(n), 1, include_ident,
-                            nullptr, d_res, c->ws[1].p, c->s_compute, err);
+    Lane& l = c->lane[LANE_ENC];
+    std::lock_guard<std::mutex> lk(l.mu);
+    CK(l.in[1].need(n + 64));
+    CK(l.compact[1].need(sb_frame_max_len(n) + 64));
+    CK(l.ws[1].need(encode_ws_bytes(n) + sizeof(sb_frame_result) + 256));
+    rc = need_pinned(l, 4, 4096, err); if (rc) return rc;
+    CK(cudaMemcpyAsync(l.in[1].p, in, n, cudaMemcpyHostToDevice, l.s_compute));
+    sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)l.ws[1].p + align_up(encode_ws_bytes(n), 256));
+    rc = compress_stream_ws(*c, l.in[1].as<uint8_t>(), n, l.compact[1].as<uint8_t>(), sb_frame_max_len(n), 1, include_ident,
+                            nullptr, d_res, l.ws[1].p, l.s_compute, err);
     if (rc) return rc;
-    sb_frame_result* res = (sb_frame_result*)c->pinned[4];
-    CK(cudaMemcpyAsync(res, d_res, sizeof *res, cudaMemcpyDeviceToHost, c->s_compute));
-    CK(cudaStreamSynchronize(c->s_compute));
+    sb_frame_result* res = (sb_frame_result*)l.pinned[4];
+    CK(cudaMemcpyAsync(res, d_res, sizeof *res, cudaMemcpyDeviceToHost, l.s_compute));
+    CK(cudaStreamSynchronize(l.s_compute));
     if (res->status.code) { if (err) *err = res->status; return (int)res->status.code; }
-    CK(cudaMemcpyAsync(out, c->compact[1].p, res->bytes, cudaMemcpyDeviceToHost, c->s_compute));
-    CK(cudaStreamSynchronize(c->s_compute));
+    CK(cudaMemcpyAsync(out, l.compact[1].p, res->bytes, cudaMemcpyDeviceToHost, l.s_compute));
+    CK(cudaStreamSynchronize(l.s_compute));
     *out_n = (size_t)res->bytes;
     ok(err);
     return 0;
@@ -984,19 +1006,20 @@ int sb_frame_decode_device(const uint8_t* d_in, uint64_t n, uint8_t* d_out, uint
     Ctx* c;
     int rc = get_ctx(&c, err);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    Lane& l = c->lane[LANE_DEC];
+    std::lock_guard<std::mutex> lk(l.mu);
     cudaStream_t st = (cudaStream_t)stream;
     uint64_t maxc = d_chunk_offs ? (uint64_t)nchunks + 1 : n / 1024 + 4096;
-    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
+    rc = need_pinned(l, 4, 4096, err); if (rc) return rc;
     for (;;) {
         if (maxc > 0xFFFFFFF0ull) return fail(err, SB_E_INVALID);
-        CK(c->ws[1].need(decode_ws_bytes(maxc) + sizeof(sb_frame_result) + 256));
-        sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)c->ws[1].p + align_up(decode_ws_bytes(maxc), 256));
+        CK(l.ws[1].need(decode_ws_bytes(maxc) + sizeof(sb_frame_result) + 256));
+        sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)l.ws[1].p + align_up(decode_ws_bytes(maxc), 256));
         sb_error e2;
-        rc = sb_frame_decode_device_ws(d_in, n, d_out, cap, d_chunk_offs, nchunks, flags, d_res, c->ws[1].p, decode_ws_bytes(maxc),
+        rc = sb_frame_decode_device_ws(d_in, n, d_out, cap, d_chunk_offs, nchunks, flags, d_res, l.ws[1].p, decode_ws_bytes(maxc),
                                        (uint32_t)maxc, st, &e2);
         if (rc) { if (err) *err = e2; return rc; }
-        sb_frame_result* res = (sb_frame_result*)c->pinned[4];
+        sb_frame_result* res = (sb_frame_result*)l.pinned[4];
         CK(cudaMemcpyAsync(res, d_res, sizeof *res, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (res->status.code == SB_E_INVALID && res->status.b == 1 && maxc < n / 8 + 16) { maxc = maxc * 8; continue; }   // chunk table too small
@@ -1016,18 +1039,19 @@ int sb_frame_decode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_
     Ctx* c;
     int rc = get_ctx(&c, err);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
-    cudaStream_t st = c->s_compute;
-    CK(c->in[1].need(n + 64));
-    rc = need_pinned(*c, 4, 4096, err); if (rc) return rc;
-    CK(cudaMemcpyAsync(c->in[1].p, in, n, cudaMemcpyHostToDevice, st));
+    Lane& l = c->lane[LANE_DEC];
+    std::lock_guard<std::mutex> lk(l.mu);
+    cudaStream_t st = l.s_compute;
+    CK(l.in[1].need(n + 64));
+    rc = need_pinned(l, 4, 4096, err); if (rc) return rc;
+    CK(cudaMemcpyAsync(l.in[1].p, in, n, cudaMemcpyHostToDevice, st));
     uint64_t maxc = n / 1024 + 4096;
-    sbk::DecodeCtl* hc = (sbk::DecodeCtl*)c->pinned[4];
+    sbk::DecodeCtl* hc = (sbk::DecodeCtl*)l.pinned[4];
     sbk::DecodePlan p;
     for (;;) {
-        CK(c->ws[1].need(decode_ws_bytes(maxc) + sizeof(sb_frame_result) + 256));
-        sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)c->ws[1].p + align_up(decode_ws_bytes(maxc), 256));
-        p = make_decode_plan(c->in[1].as<uint8_t>(), n, nullptr, out ? cap : ~0ull, nullptr, 0, 0, d_res, c->ws[1].p, (uint32_t)maxc);
+        CK(l.ws[1].need(decode_ws_bytes(maxc) + sizeof(sb_frame_result) + 256));
+        sb_frame_result* d_res = (sb_frame_result*)((uint8_t*)l.ws[1].p + align_up(decode_ws_bytes(maxc), 256));
+        p = make_decode_plan(l.in[1].as<uint8_t>(), n, nullptr, out ? cap : ~0ull, nullptr, 0, 0, d_res, l.ws[1].p, (uint32_t)maxc);
         rc = decode_index_phase(*c, p, st, err);
         if (rc) return rc;
         CK(cudaMemcpyAsync(hc, p.ctl, sizeof(sbk::DecodeCtl), cudaMemcpyDeviceToHost, st));
@@ -1039,14 +1063,14 @@ int sb_frame_decode(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_
     // Sizing call: only possible failures that precede any data check are reported by the full call.
     if (!out) { *out_n = (size_t)produced; ok(err); return 0; }
     if (produced > cap) return fail(err, SB_BUFFER_TOO_SMALL, cap, produced);
-    CK(c->compact[1].need(produced + 64));
-    p.out = c->compact[1].as<uint8_t>();
+    CK(l.compact[1].need(produced + 64));
+    p.out = l.compact[1].as<uint8_t>();
     rc = decode_payload_phase(*c, p, st, err);
     if (rc) return rc;
-    sb_frame_result* res = (sb_frame_result*)((uint8_t*)c->pinned[4] + 512);
+    sb_frame_result* res = (sb_frame_result*)((uint8_t*)l.pinned[4] + 512);
     CK(cudaMemcpyAsync(res, p.result, sizeof *res, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (res->bytes) CK(cudaMemcpy(out, c->compact[1].p, res->bytes, cudaMemcpyDeviceToHost));
+    if (res->bytes) CK(cudaMemcpy(out, l.compact[1].p, res->bytes, cudaMemcpyDeviceToHost));
     *out_n = (size_t)res->bytes;
     if (res->status.code) { if (err) *err = res->status; return (int)res->status.code; }
     ok(err);
