@@ -732,7 +732,8 @@ def run_frame(args, local_rank):
     from oracle import oracle as orc
     span = len(text) - BLOCK
     head = b"".join(text[(i * MUL) % span:][:BLOCK] for i in range(4))
-    ck(L.sb_frame_encode_device_ws(t_pool.data_ptr(), wave_bytes, t_enc.data_ptr(), cap, 1, t_idx.data_ptr(), t_res.data_ptr(),
+    d0 = _wave_input(L, snap, torch, t_text, len(text), t_pool, pool_waves, wave_bytes, 0, 0, stream, err, generated)   # wave 0 again (the pool cycles)
+    ck(L.sb_frame_encode_device_ws(d0, wave_bytes, t_enc.data_ptr(), cap, 1, t_idx.data_ptr(), t_res.data_ptr(),
                                    t_scr.data_ptr(), esb + 256, stream, C.byref(err)))
     torch.cuda.synchronize()
     want = orc.frame_encode(head)
