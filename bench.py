@@ -707,23 +707,25 @@ def run_frame(args, local_rank):
             ck(L.sb_frame_encode_device_ws(d_in, wave_bytes, t_enc.data_ptr(), cap, 1 if w == 0 else 0, t_idx.data_ptr(),
                                            t_res.data_ptr(), t_scr.data_ptr(), esb + 256, stream, C.byref(err)))
             e1.record()
-            # the decoder takes the stream length from the index the encoder just wrote (t_idx[W]), all on the device:
-            # cap is the only host-side size
-            n_stream = int(t_idx[W].item()) if verify else one_pass.sizes[w]
+            # the stream length is the last entry of the index the encoder just wrote (one 8-byte read back per wave;
+            # the pool cycles, so sizes from an earlier pass are not this wave's)
+            n_stream = int(t_idx[W].item())
             ck(L.sb_frame_decode_device_ws(t_enc.data_ptr(), n_stream, t_dec.data_ptr(), wave_bytes, t_idx.data_ptr(), W,
                                            0 if w == 0 else 1, t_res.data_ptr() + 64, t_scr.data_ptr(), dsb + 256, W + 1, stream,
                                            C.byref(err)))
             e2.record()
             marks.append((e0, e1, e2))
+            one_pass.sizes[w] = n_stream
             if verify:
                 torch.cuda.synchronize()
-                one_pass.sizes[w] = n_stream
                 assert int(t_res[0].item()) & 0xFFFFFFFF == 0 and int(t_res[8].item()) & 0xFFFFFFFF == 0, \
                     "frame status != Ok: wave %d encode %r decode %r" % (w, t_res[:6].tolist(), t_res[8:14].tolist())
                 assert int(t_res[12].item()) == wave_bytes, "decoder produced %d bytes" % int(t_res[12].item())
                 assert torch.equal(t_dec[:wave_bytes], t_pool[(w % pool_waves) * wave_bytes:(w % pool_waves + 1) * wave_bytes]), "frame round trip mismatch"
             total_stream += one_pass.sizes[w]
         torch.cuda.synchronize()
+        bad = t_res[8].item() & 0xFFFFFFFF
+        assert bad == 0, "frame decode status %d in the last wave" % bad
         return sum(a.elapsed_time(b) for a, b, _ in marks), sum(b.elapsed_time(c) for _, b, c in marks), total_stream
 
     one_pass.sizes = [0] * nwaves
