@@ -557,8 +557,11 @@ def frame_shard_measure(args, snap, L, torch, dev, rank, world, t_text, text_len
     generated = {}
     first_wave_hash = {}
 
+    fake = os.environ.get("SNAPB200_FAKE_SHARD")                     # debugging: "rank/world" whose data this single rank generates
+    frank, fworld = (int(x) for x in fake.split("/")) if fake else (None, world)
+
     def chunk0(w, r):
-        return (w * world + r) * W                                   # first global chunk of (wave, rank)
+        return (w * fworld + (frank if frank is not None else r)) * W   # first global chunk of (wave, rank)
 
     def run(exchange, check=False):
         state = {"ok": True}

@@ -126,7 +126,9 @@ SB_DEVICE uint32_t k1_extend(const uint8_t* win, uint32_t n, uint32_t s, uint32_
         uint32_t m = 0;
         if (p < n) {
             const uint32_t avail = n - p;
-            const uint32_t x = k1_rd32_end(win, p, n) ^ k1_rd32(win, c + 4 * lane);
+            // the candidate side sits below p, but its aligned two-word read may reach 6 bytes past it: near the end of
+            // the block (= possibly the end of the caller's allocation) both sides use the bounded read
+            const uint32_t x = k1_rd32_end(win, p, n) ^ (p + 8 <= n ? k1_rd32(win, c + 4 * lane) : k1_rd32_end(win, c + 4 * lane, n));
             m = x ? (uint32_t)(ffs(x) - 1) >> 3 : 4;
             if (m > avail) m = avail;
         }

@@ -753,3 +753,33 @@ def test_streaming_wrappers_batch_mode(snap, oracle):
                 assert b"".join(parts) == want[1]
             else:
                 assert data.startswith(b"".join(parts))
+
+
+def test_k1_reads_stay_inside_the_input(snap, oracle):
+    """Blocks whose final copy runs to the very end of the block, in a tensor that ends exactly there: K1 must not read
+    past the caller's allocation (round 2: k1_extend's candidate side over-read up to 6 bytes, which faulted on rank 4
+    of an 8-GPU run where the next page was unmapped). Bit-exactness here; tools/sanitize.sh runs this test under
+    memcheck with the caching allocator off, so that the allocation really ends at the last byte."""
+    import ctypes as C
+    import torch
+    import gpu_helpers
+    L = gpu_helpers.lib()
+    dev = torch.device("cuda:0")
+    base = corpus("alice29.txt")
+    blocks = []
+    for k, tail in enumerate((17, 64, 200, 1000, 4, 5, 6, 7, 8, 9, 31, 33)):
+        b = bytearray(base[k * 1000:k * 1000 + 65536])
+        b[-tail:] = b[100:100 + tail]                       # the block ends inside a match against earlier text
+        blocks.append(bytes(b))
+    blocks.append(bytes(65536))                             # one long run to the end
+    n = len(blocks)
+    t_in = torch.frombuffer(bytearray(b"".join(blocks)), dtype=torch.uint8).to(dev)      # exactly n * 65536 bytes
+    t_out = torch.zeros(n * 76544, dtype=torch.uint8, device=dev)
+    lens = torch.zeros(n, dtype=torch.int32, device=dev)
+    b = gpu_helpers.batch_from_tensors(t_in, 65536, 65536, t_out, 76544, 76544, lens, None, n)
+    e = snap._lib.SbError()
+    assert L.sb_compress_batch_device(C.byref(b), torch.cuda.current_stream().cuda_stream, C.byref(e)) == 0
+    torch.cuda.synchronize()
+    out = t_out.cpu().numpy()
+    for i, blk in enumerate(blocks):
+        assert bytes(out[i * 76544:i * 76544 + int(lens[i])]) == oracle.compress(blk), i
