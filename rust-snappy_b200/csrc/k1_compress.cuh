@@ -93,19 +93,20 @@ struct K1Prod {
     uint32_t published;   // value of ctrl[0]
     uint32_t tail_seen;   // last value read from ctrl[1]
 };
-static const uint32_t K1_PUBLISH = 64;   // a publish is a release store behind the event stores (~0.5k cycles): amortise it
+static const uint32_t K1_PUBLISH = 64;   // a publish costs a CTA fence behind global stores (~0.5k cycles): amortise it
 
 SB_DEVICE void k1_publish(const K1Ring& r, K1Prod& pr) {
     if (pr.published == pr.head) return;
-    syncwarp();                                           // every lane's event stores happen-before lane 0's release
-    if (lane_id() == 0) st_release(&r.ctrl[0], pr.head);
+    threadfence_block();                                  // EVERY lane fences its own event stores (CTA scope) ...
+    syncwarp();                                           // ... before lane 0 makes the new head visible
+    if (lane_id() == 0) st_volatile(&r.ctrl[0], pr.head);
     pr.published = pr.head;
 }
 SB_DEVICE void k1_wait_space(const K1Ring& r, K1Prod& pr, uint32_t need) {
     if (pr.head + need - pr.tail_seen <= r.size) return;
     k1_publish(r, pr);                                   // the emitter must see everything before we wait on it
     for (;;) {
-        pr.tail_seen = shfl(ld_acquire(&r.ctrl[1]), 0);    // one reader: the decision must be warp-uniform
+        pr.tail_seen = shfl(ld_volatile(&r.ctrl[1]), 0);   // one reader: the decision must be warp-uniform
         if (pr.head + need - pr.tail_seen <= r.size) return;
         spin();
     }
@@ -493,13 +494,13 @@ SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, c
     for (;;) {
         uint32_t avail;
         for (;;) {
-            avail = ld_acquire(&ring.ctrl[0]) - tail;
+            avail = ld_volatile(&ring.ctrl[0]) - tail;
             avail = shfl(avail, 0);
             if (avail) break;
             spin_long();
         }
         const uint32_t m = avail < 32 ? avail : 32;
-        syncwarp();                                           // lane 0's acquire happens-before every lane's event loads
+        threadfence_block();                                  // every lane: the event loads below stay behind the head read
         uint64_t ev = 0;
         if (lane < m) ev = ld_volatile64(&ring.ev[(tail + lane) & (ring.size - 1)]);   // the ring may live in global memory
         const uint32_t pos = (uint32_t)(ev & 0x1FFFFu), len = (uint32_t)((ev >> 17) & 0x1FFFFu), off = (uint32_t)(ev >> 34);
@@ -557,7 +558,7 @@ SB_DEVICE uint32_t k1_emit_block(const uint8_t* win, uint8_t* out, uint32_t d, c
         prev_end = shfl(pos + len, m - 1);
         tail += m;
         syncwarp();
-        if (lane == 0) st_release(&ring.ctrl[1], tail);        // the batch's event loads (all lanes, before the syncwarp above) are done
+        if (lane == 0) st_volatile(&ring.ctrl[1], tail);
         if (any(is_end)) return d;
     }
 }

@@ -73,15 +73,6 @@ SB_DEVICE void spin_long() { __nanosleep(1500); }
 SB_DEVICE uint32_t ld_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 SB_DEVICE void st_volatile(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
 SB_DEVICE uint64_t ld_volatile64(const uint64_t* p) { return *(const volatile uint64_t*)p; }
-// release/acquire at CTA scope: the hand-off words of the parser -> emitter ring (k1_compress.cuh). A release store
-// orders every earlier write of the thread (and, after a __syncwarp, of its warp) before it; an acquire load orders
-// every later read after it -- the PTX memory model's message-passing pattern, no fence needed around them.
-SB_DEVICE void st_release(uint32_t* p, uint32_t v) { asm volatile("st.release.cta.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-SB_DEVICE uint32_t ld_acquire(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.cta.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // read-only / streaming global accessors
 SB_DEVICE uint32_t ldg32(const void* p) { return __ldg((const uint32_t*)p); }

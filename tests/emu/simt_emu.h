@@ -191,8 +191,6 @@ SB_DEVICE void spin_long() { sbemu::yield(); }
 SB_DEVICE uint32_t ld_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 SB_DEVICE void st_volatile(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
 SB_DEVICE uint64_t ld_volatile64(const uint64_t* p) { return *(const volatile uint64_t*)p; }
-SB_DEVICE void st_release(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
-SB_DEVICE uint32_t ld_acquire(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 
 SB_DEVICE uint32_t ldg32(const void* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 SB_DEVICE uint4 ldg128(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }
