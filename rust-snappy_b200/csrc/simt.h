@@ -10,7 +10,10 @@
 #include <stddef.h>
 
 #if defined(SB_EMU)
-#include "../../tests/emu/simt_emu.h"
+// the emulator build (tests/emu/emu_kernels.cpp) includes its own simt_emu.h BEFORE any kernel header
+#ifndef SB_EMU_PRIMITIVES
+#error "SB_EMU builds must include tests/emu/simt_emu.h first (it defines the warp primitives)"
+#endif
 #else
 
 #include <cuda_runtime.h>

@@ -2,6 +2,7 @@
 // rust-snappy_b200/csrc with g++ against the fiber warp emulator and exposes
 // them to pytest through a C interface (tests/test_emu_kernels.py).
 #define SB_EMU 1
+#include "simt_emu.h"
 #include "../../rust-snappy_b200/csrc/k1_compress.cuh"
 #include "../../rust-snappy_b200/csrc/k2_decompress.cuh"
 

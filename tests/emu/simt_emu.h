@@ -5,6 +5,7 @@
 // another; warp collectives are rendezvous points between the 32 fibers of a
 // warp. It checks logic, not memory-model races and not performance.
 #pragma once
+#define SB_EMU_PRIMITIVES 1
 #include <stdint.h>
 #include <stddef.h>
 #include <stdlib.h>
