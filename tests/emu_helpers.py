@@ -116,3 +116,39 @@ def decompress_units(streams, caps, grid=1, block=32):
                     bytes(out[ooffs[i]:ooffs[i] + int(out_lens[i])]),
                     bytes(out[ooffs[i] + ocap[i]:ooffs[i] + ocap[i] + 16])))
     return res
+
+
+class SbFrameResult(C.Structure):
+    _fields_ = [("status", SbError), ("bytes", C.c_uint64), ("nchunks", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+def frame_encode(data, ident=True):
+    """K4 assembly around K1 (with the fused chunk checksum) under the emulator: (stream, chunk offsets, result)."""
+    n = len(data)
+    src = np.frombuffer(bytes(data) + b"\0" * 16, dtype=np.uint8).copy()
+    nchunks = (n + 65535) // 65536
+    cap = 10 + nchunks * (8 + 76490)
+    out = np.full(cap + 16, 0xEE, dtype=np.uint8)
+    offs = np.zeros(nchunks + 2, dtype=np.uint64)
+    res = SbFrameResult()
+    lib().emu_frame_encode(C.c_void_p(src.ctypes.data), C.c_uint64(n), C.c_void_p(out.ctypes.data), C.c_uint64(cap), 1 if ident else 0,
+                           C.c_void_p(offs.ctypes.data), C.byref(res))
+    return bytes(out[:res.bytes]), [int(x) for x in offs[:nchunks + 1]], res
+
+
+def frame_decode(stream, cap, index=None, fragment=False, max_chunks=None):
+    """K5 (parse or walk, scan, decode + checksum, finish) under the emulator: (status tuple, produced bytes)."""
+    n = len(stream)
+    src = np.frombuffer(bytes(stream) + b"\0" * 16, dtype=np.uint8).copy()
+    out = np.full(cap + 16, 0xEE, dtype=np.uint8)
+    res = SbFrameResult()
+    idx = np.array(index, dtype=np.uint64) if index is not None else None
+    nidx = len(index) - 1 if index is not None else 0
+    maxc = max_chunks if max_chunks is not None else max(nidx + 1, n // 8 + 16)
+    lib().emu_frame_decode(C.c_void_p(src.ctypes.data), C.c_uint64(n), C.c_void_p(out.ctypes.data), C.c_uint64(cap),
+                           C.c_void_p(idx.ctypes.data) if idx is not None else None, nidx, 1 if fragment else 0, C.byref(res), maxc)
+    assert bytes(out[cap:cap + 16]) == b"\xee" * 16
+    e = res.status
+    status = (ERR.get(e.code, {10: "StreamHeader", 11: "StreamHeaderMismatch", 12: "UnsupportedChunkType", 13: "UnsupportedChunkLength",
+                                14: "Checksum", 100: "UnexpectedEof", 202: "Invalid"}.get(e.code, str(e.code))), e.a, e.b, e.c)
+    return status, bytes(out[:res.bytes]), res

@@ -115,3 +115,62 @@ def test_k2_adversarial_blocks(oracle):
     units = adversarial_blocks()
     res = emu.decompress_units([oracle.compress(u) for u in units], [len(u) for u in units], grid=2, block=128)
     assert [i for i, (r, u) in enumerate(zip(res, units)) if r[0][0] != "Ok" or r[1] != u or r[2] != b"\xee" * 16] == []
+
+
+def _frame_err(e):
+    """Oracle error tuple -> the (name, a, b, c) shape of the emulated result record."""
+    name = e[0]
+    if name == "StreamHeaderMismatch":
+        return (name, int.from_bytes(e[1], "little") if isinstance(e[1], (bytes, bytearray)) else e[1], 0, 0)
+    return tuple(e)
+
+
+def test_k4_frame_encode_matches_write_frame_encoder(oracle):
+    """fill lens -> K1 with the chunk CRC in the emitter -> two-level scan -> gather == write::FrameEncoder bytes."""
+    for name, cut in (("alice29.txt", 150000), ("fireworks.jpeg", 70000), ("html", 65536), ("geo.protodata", 1), ("paper-100k.pdf", 66000)):
+        data = corpus(name)[:cut]
+        stream, offs, res = emu.frame_encode(data)
+        assert res.status.code == 0 and res.nchunks == (len(data) + 65535) // 65536
+        assert stream == oracle.frame_encode(data), name
+        assert offs[0] == 10 and offs[-1] == len(stream)
+    stream, offs, res = emu.frame_encode(corpus("lcet10.txt")[:140000], ident=False)
+    assert stream == oracle.frame_encode(corpus("lcet10.txt")[:140000])[10:] and offs[0] == 0
+
+
+def test_k5_frame_decode_index_walk_and_errors(oracle):
+    """K5 under the emulator: parallel parse over the encoder's index, the serial walk, identifier-less fragments, and
+    the reference's first error in stream order with the bytes before it."""
+    from oracle.oracle import OracleError
+    data = corpus("alice29.txt")[:150000]
+    good = oracle.frame_encode(data)
+    stream, offs, _ = emu.frame_encode(data)
+    assert stream == good
+    for kw in (dict(index=offs), dict(index=None), dict(index=[10, 50, len(good)])):          # last: wrong index -> serial walk
+        st, out, res = emu.frame_decode(good, len(data), **kw)
+        assert st[0] == "Ok" and out == data and res.nchunks == 3, kw
+    frag = good[10:]
+    st, out, _ = emu.frame_decode(frag, len(data), index=[o - 10 for o in offs], fragment=True)
+    assert st[0] == "Ok" and out == data
+    assert emu.frame_decode(frag, len(data))[0][0] == "StreamHeader"
+    st, out, _ = emu.frame_decode(good, 1000)
+    assert st[:3] == ("BufferTooSmall", 1000, len(data)) and out == b""
+    st, out, _ = emu.frame_decode(good, len(data), max_chunks=2)                                # chunk table too small
+    assert st[0] == "Invalid" and st[2] == 1
+    ident = b"\xff\x06\x00\x00sNaPpY"
+    flip = bytearray(good); flip[len(good) // 2] ^= 0x10
+    crc = bytearray(good); crc[14] ^= 1
+    streams = [bytes(flip), bytes(crc), good[:-7], good + b"\x00\x07", ident + b"\x02\x00\x00\x00", b"123",
+               ident + b"\x80\x03\x00\x00xyz" + b"\xfe\x02\x00\x00\x00\x00" + ident + good[10:],
+               ident + b"\x00\x05\x00\x00\x00\x00\x00\x00\x80", ident + b"\x01\x03\x00\x00abc", b"\xff\x05\x00\x00sNaPp",
+               b"\xff\x06\x00\x00sNaPpZ", ident + b"\x00\xff\xff\xff", ident + b"\x00\x04\x00\x00\x00\x00\x00\x00"]
+    for s in streams:
+        try:
+            want = (("Ok", 0, 0, 0), oracle.frame_decode(s))
+        except OracleError as e:
+            want = (_frame_err(e.err), None)
+        st, out, _ = emu.frame_decode(s, 200000)
+        assert st == want[0], (s[:20], st, want[0])
+        if want[1] is not None:
+            assert out == want[1]
+        else:
+            assert data.startswith(out)
