@@ -221,8 +221,8 @@ def run_ours(args, rank, local_rank, world):
     snap = graft.load_package()
     L = snap._lib.lib()
     err = snap._lib.SbError()
-    # this rank's host thread (and the pinned buffers it allocates from here on) stay on the GPU's NUMA node
-    numa_node = L.sb_bind_host_thread_to_device_numa(local_rank) if not args.no_numa_bind else -2
+    numa_node = {"node": None}       # filled by run_e2e: the host thread is bound to the GPU's NUMA node only while it
+                                     # allocates and streams pinned memory; the CPU-side work (parity, cpu_baseline) keeps every core
     text = load_text()
     span = len(text) - BLOCK
     blocks = args.blocks
@@ -366,7 +366,14 @@ def run_ours(args, rank, local_rank, world):
     # ---------------- e2e: host buffers through the C ABI (H2D/D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, snap, L, torch, dev, t_in, t_clen, rank, world)
+        aff0 = os.sched_getaffinity(0)
+        if not args.no_numa_bind:
+            # this rank's host thread (and the pinned buffers it allocates from here on) stay on the GPU's NUMA node
+            numa_node["node"] = L.sb_bind_host_thread_to_device_numa(local_rank)
+        try:
+            e2e = run_e2e(args, snap, L, torch, dev, t_in, t_clen, rank, world)
+        finally:
+            os.sched_setaffinity(0, aff0)
 
     # ---------------- N > 1: the frame path's exchange step (sizes + payload all-gather over NCCL), small scale
     shard = None
@@ -396,7 +403,7 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": "batched raw block compress+decompress: %d x 64KB synthetic text blocks per GPU (BASELINE configs[1])" % blocks,
                    "blocks_per_gpu": blocks, "block_bytes": BLOCK, "wave_blocks": wave, "ratio": comp_bytes / u_rank,
                    "l2": "inputs larger than L2 (%.1f GiB per GPU per pass)" % (u_rank / 2**30), "parity": parity,
-                   "wall_s_timed_region": wall, "numa_node": numa_node,
+                   "wall_s_timed_region": wall, "numa_node": numa_node["node"],
                    "lib": os.path.basename(os.environ.get("SNAPB200_LIB", "libsnapb200.so")),
                    "k1_ng_env": os.environ.get("SNAPB200_K1_NG")},
         "compress_gbs": u_all * args.steps / (ms_cmax / 1e3) / 1e9,
