@@ -218,6 +218,11 @@ def run_ours(args, rank, local_rank, world):
         # keep stdout for the one JSON line: NCCL's banner/debug output goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+        # finish communicator / connection setup before the first codec kernel runs: NCCL sets transports up lazily at the
+        # first collective, and nothing of that should be in flight beside K1 (the 8-GPU faults of round 2 all hit a rank
+        # whose first kernels ran right after init)
+        dist.barrier()
+        torch.cuda.synchronize()
     snap = graft.load_package()
     L = snap._lib.lib()
     err = snap._lib.SbError()
@@ -650,6 +655,8 @@ def run_frame_shard(args, rank, local_rank, world):
         import torch.distributed as dist
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()                   # communicator setup done before the first codec kernel (see run_ours)
+        torch.cuda.synchronize()
     snap = graft.load_package()
     L = snap._lib.lib()
     text = load_text()

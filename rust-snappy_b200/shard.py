@@ -151,6 +151,12 @@ class WavePipeline:
         gcap = self.cap * self.world if exchange else 0
         self.gathered = [torch.empty(gcap + 16, dtype=torch.uint8, device=device) for _ in range(2)] if exchange and self.world > 1 else None
         self.err = _lib.SbError()
+        if self.gathered is not None:
+            # bring the point-to-point transports up now (NCCL connects peers lazily at the first send/recv): one byte
+            # to and from every peer, so that no connection setup runs beside the first waves' kernels
+            warm = torch.zeros(self.world, dtype=torch.uint8, device=device)
+            exchange_payload(warm, [1] * self.world, self.gathered[0], 0, dist)
+            torch.cuda.synchronize()
         self.pending = None          # (wave, buffer index) encoded but not exchanged yet
         self.works = [[], []]        # outstanding exchanges per buffer
         self.stream_bytes = 0        # bytes of the reassembled stream so far (all ranks, all finished waves)
